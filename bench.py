@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- SRF routing-layer throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg3|cfg2|cfg1] [--impl reference]
+
+A "step" is one forward pass of the routing stack (primary capsules -> CTC logits,
+tfsr/model/sequence_router_naive.py:145-193) over one synthetic batch.  Default workload is
+cfg-3 of BASELINE.json (SRF-SDR WSJ-shaped, 31 labels + blank, batch 64 x 1500 fbank frames
+= 64 x 375 routing frames, ITER=1), the configuration the metric "frames/sec at 1/2/4/8
+B200" is quoted on.  Multi-GPU: utterances are independent, every rank routes its own
+64-utterance shard with no data-path collective (weak scaling); value = all ranks' routing
+frames / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: enc_num, PH, CH, class_n, DIM, lpad, rpad, iters, sdr, B, T(fbank frames)
+    "cfg1": dict(desc="SRF-SDR TIMIT-shaped, ITER=1, L7 PH60 CH30 DIM8 w3 cls63, B=8 x T=300",
+                 L=7, PH=60, CH=30, class_n=63, DIM=8, lpad=1, rpad=1, iters=1, sdr=True, B=8, T=300),
+    "cfg2": dict(desc="SRF-DR TIMIT-shaped, ITER=3, LPAD=RPAD=3, L7 PH60 CH30 DIM8 cls63, B=8 x T=300",
+                 L=7, PH=60, CH=30, class_n=63, DIM=8, lpad=3, rpad=3, iters=3, sdr=False, B=8, T=300),
+    "cfg3": dict(desc="SRF-SDR WSJ-shaped, ITER=1, L10 PH60 CH30 DIM20 w5 cls32, B=64 x T=1500",
+                 L=10, PH=60, CH=30, class_n=32, DIM=20, lpad=2, rpad=2, iters=1, sdr=True, B=64, T=1500),
+}
+
+
+def shapes_of(w):
+  from srf_b200 import layer_shapes
+  return layer_shapes(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"],
+                      w["lpad"] + w["rpad"] + 1)
+
+
+def algorithmic_work(w):
+  """Per routing frame: F_uhat = 2 I O D d, F_route = 4 ITER I O D (SDR) /
+  (4 ITER - 2) I O D (DR), bytes = 4 (H d + O D) per layer; weights once per launch."""
+  window = w["lpad"] + w["rpad"] + 1
+  f_uhat = f_route = bytes_frame = weights = 0
+  for (I, O, D, d) in shapes_of(w):
+    f_uhat += 2 * I * O * D * d
+    f_route += (4 * w["iters"] if w["sdr"] else 4 * w["iters"] - 2) * I * O * D
+    bytes_frame += 4 * (I // window * d + O * D)
+    weights += 4 * (I * O * D * d + I * O * D)
+  return f_uhat, f_route, bytes_frame, weights
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clock and throttle reasons of one GPU during the timed region."""
+  REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+             0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+    self._stop_evt = threading.Event()
+    self.ok = False
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+      self.ok = True
+    except Exception:  # pylint: disable=broad-except
+      self.ok = False
+
+  def run(self):
+    if not self.ok:
+      return
+    while not self._stop_evt.is_set():
+      try:
+        self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        try:
+          mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:  # pylint: disable=broad-except
+          mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in self.REASONS.items():
+          if mask & bit:
+            self.reasons.add(name)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop_evt.wait(0.05)
+
+  def stop(self):
+    self._stop_evt.set()
+    self.join(timeout=2)
+    s = sorted(self.samples)
+    return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_run(w, n_utts, n_frames, repeats=1, seed=0):
+  """The reference's CPU path: TensorFlow is not installable here, so this
+  times the oracle port (torch CPU fp32 restatement of naive:145-193) on all host threads."""
+  from oracle import srf_oracle as o
+  torch.set_num_threads(os.cpu_count() or 1)
+  shapes = shapes_of(w)
+  p = o.init_params(shapes, w["class_n"], seed=seed)
+  emb = torch.randn(n_utts, n_frames, w["PH"], w["DIM"], generator=torch.Generator().manual_seed(seed))
+  best = None
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    o.route_stack(emb, p, w["lpad"], w["rpad"], w["iters"], w["sdr"])
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return n_utts * n_frames / best, best
+
+
+def cpu_sample_shape(w):
+  # ~10-30 s of CPU work: per-frame cost is independent of S; B kept >= 4 so the CPU ops batch
+  if w["DIM"] >= 16:
+    return 4, 64
+  return w["B"], 75
+
+
+def run_reference_arm(args, w, rank, world):
+  if rank != 0:
+    return
+  n_utts, n_frames = cpu_sample_shape(w)
+  times = []
+  for i in range(args.warmup + args.steps):
+    fps, dt = cpu_reference_run(w, n_utts, n_frames)
+    if i >= args.warmup:
+      times.append(dt)
+  ms = 1e3 * sum(times) / len(times)
+  value = n_utts * n_frames / (ms / 1e3)
+  sample = "%d utterances x %d routing frames of the %s model per step" % (n_utts, n_frames, args.workload)
+  line = {
+      "impl": "reference", "metric": "routing_frames_per_sec", "value": value, "unit": "routing frames/s",
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": w["desc"], "sample": sample,
+                 "note": "reference needs TensorFlow (not installable offline): oracle port timed"},
+      "cpu_baseline": {"value": value, "unit": "routing frames/s", "cores": os.cpu_count(),
+                       "kind": "port", "sample": sample},
+      "e2e": {"value": value, "unit": "routing frames/s", "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--uhat", default="fp32", choices=["fp32", "tf32", "bf16"])
+  args = ap.parse_args()
+  w = dict(WORKLOADS[args.workload])
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+  if args.impl == "reference":
+    run_reference_arm(args, w, rank, world)
+    return
+
+  if args.warmup < 3:
+    args.warmup = 3
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py: no CUDA device; the routing path has no CPU fallback "
+                     "(use --impl reference for the CPU arm)")
+  import torch.distributed as dist
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  from srf_b200 import RoutingStack
+  B, S = w["B"], (w["T"] + 3) // 4
+  stack = RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"],
+                       w["lpad"], w["rpad"], w["iters"], w["sdr"], device=dev, seed=0,
+                       uhat_mode=args.uhat)
+  g = torch.Generator().manual_seed(1000 + rank)
+  n_bufs = 2
+  host_emb = [torch.randn(B, S, w["PH"], w["DIM"], generator=g).pin_memory() for _ in range(n_bufs)]
+  dev_emb = [h.to(dev) for h in host_emb]
+  logits = torch.empty(B, S, w["class_n"], device=dev)
+  host_logits = torch.empty(B, S, w["class_n"]).pin_memory()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(steps):
+      fn(i)
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end)
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = t.item()
+    return ms
+
+  def step_resident(i):
+    stack.forward(dev_emb[i % n_bufs], out_logits=logits)
+
+  def step_e2e(i):
+    out = stack.forward(host_emb[i % n_bufs], out_logits=logits)   # H2D inside forward
+    host_logits.copy_(out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()                      # result is on the host
+
+  for i in range(args.warmup):
+    step_resident(i)
+  l0 = stack.handle.launches
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  ms_total = timed(step_resident, args.steps)
+  launches = stack.handle.launches - l0
+  for i in range(2):
+    step_e2e(i)
+  ms_e2e = timed(step_e2e, args.steps)
+  clocks = sampler.stop()
+  kernel_name = stack.handle.last_kernel
+
+  frames_step = B * S * world
+  ms_step = ms_total / args.steps
+  value = frames_step / (ms_step / 1e3)
+  e2e_value = frames_step / (ms_e2e / args.steps / 1e3)
+
+  peaks = {}
+  try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+      peaks = json.load(f)
+  except Exception:  # pylint: disable=broad-except
+    pass
+  p_tensor = peaks.get("bf16_tflops_sustained", 1400.0)
+  p_hbm = peaks.get("hbm_gbs", 6650.0)
+  peak_src = "measured" if peaks else "fallback"
+  f_uhat, f_route, bytes_frame, weights = algorithmic_work(w)
+  n_layers = w["L"]
+  t_launch = ms_step / 1e3 / n_layers                    # average routing-layer launch
+  frames_rank = B * S
+  achieved_tf = f_uhat * frames_rank / n_layers / t_launch / 1e12
+  sm_mhz = clocks.get("sm_mhz") or 1965
+  fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+  roofline = {
+      "bound": "tensor", "achieved": achieved_tf, "peak": p_tensor, "unit": "TFLOP/s",
+      "frac": achieved_tf / p_tensor, "traffic": None, "peak_source": peak_src,
+      "kernel": kernel_name, "launch_ms": t_launch * 1e3,
+      "hbm_frac": (bytes_frame * frames_rank + weights) / (ms_step / 1e3) / 1e9 / p_hbm,
+      "fp32_route_frac": f_route * frames_rank / (ms_step / 1e3) / 1e12 / fp32_peak,
+      "note": "achieved = u_hat FLOPs (2 I O D d per frame-layer) / avg layer-launch time; "
+              "u_hat runs on %s in this build" % ("FP32 CUDA cores" if args.uhat == "fp32" else "tcgen05"),
+  }
+
+  line = {
+      "metric": "routing_frames_per_sec", "value": value, "unit": "routing frames/s",
+      "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f32" if args.uhat == "fp32" else args.uhat, "data": "synthetic",
+      "config": {"workload": w["desc"], "global_batch": B * world, "routing_frames_per_utt": S,
+                 "fbank_frames_per_sec": value * 4, "parallelism": "dp%d (utterance shards, no collective)" % world,
+                 "l2": "working set per step (inputs %d MB x2 rotating + weights %d MB + intermediates) > 126 MB L2"
+                       % (host_emb[0].numel() * 4 >> 20, weights >> 20)},
+      "e2e": {"value": e2e_value, "unit": "routing frames/s",
+              "h2d_bytes_per_step": host_emb[0].numel() * 4 * world,
+              "d2h_bytes_per_step": host_logits.numel() * 4 * world},
+      "gpu_launches": launches,
+      "clocks": clocks,
+      "roofline": roofline,
+  }
+  if rank == 0 and not args.no_cpu_baseline and world == 1:
+    n_utts, n_frames = cpu_sample_shape(w)
+    fps, dt = cpu_reference_run(w, n_utts, n_frames)
+    line["cpu_baseline"] = {"value": fps, "unit": "routing frames/s", "cores": os.cpu_count(),
+                            "kind": "port",
+                            "sample": "%d utterances x %d routing frames of the same model, %.1f s"
+                                      % (n_utts, n_frames, dt)}
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,116 @@
+/*
+ * srf_b200.h -- C-ABI of the B200-native SRF capsule-routing hot path.
+ *
+ * The reference (sephiroce/srf) has no FFI / plugin layer: its boundary is the
+ * Keras model class tfsr/model/sequence_router_naive.py:33 (SequenceRouter), whose
+ * `call` (naive:120-193) executes the routing stack as stock TF ops.  The entry
+ * points below are what a ctypes binding for that path binds instead; each one
+ * cites the reference lines it replaces.  Plain C types only, no exceptions cross
+ * the boundary, every pointer that is not marked "host" is a DEVICE pointer to
+ * contiguous row-major float32 owned by the caller's tensor framework and only
+ * borrowed for the duration of the call (DLPack / data_ptr interchange).
+ *
+ * Return convention: 0 = ok; negative = invalid argument (shape/dtype/config);
+ * positive = CUDA / NCCL error code.  srf_last_error() returns the message.
+ * All compute entry points are asynchronous on the given cudaStream_t (passed
+ * as void*; NULL = legacy default stream).  One handle per device; a handle may
+ * be used from one host thread at a time.
+ */
+#ifndef SRF_B200_H_
+#define SRF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRF_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef struct srf_handle srf_handle;
+
+/* u_hat arithmetic: how the prediction vectors W.x+b are formed (north_star knob). */
+enum {
+  SRF_UHAT_FP32 = 0, /* FP32 FFMA on CUDA cores, fp32 weights                     */
+  SRF_UHAT_TF32 = 1, /* tensor cores, TF32 operands, fp32 accumulate (tcgen05)     */
+  SRF_UHAT_BF16 = 2  /* tensor cores, BF16 operands, fp32 accumulate (tcgen05)     */
+};
+
+/*
+ * One routing layer = naive:145-191 for one value of the layer index i:
+ *   window gather (naive:150-151) -> u_hat = W.x + bias (naive:154-159) ->
+ *   SDR scan (naive:162-170, body_context :232-245, pad_body_context :213-229) or
+ *   DR (naive:171-185, _loop_body :200-206) -> LayerNorm over O*D + dropout
+ *   (naive:188-191) -> optionally the head ln_o(length(.)) (naive:193).
+ *
+ * Layouts (the reference's einsum layout is canonical, einsum:82-97):
+ *   emb          [B,S,H,d]     input capsules
+ *   W            [I,O,D,d]     I = (lpad+rpad+1)*H, input capsule index i = w*H + h
+ *   bias         [I,O,D]
+ *   ln_gamma/beta[O*D]         ln_mid%d; NULL,NULL = skip the LayerNorm (raw capsules out)
+ *   dropout_mask [B,S,O,D]     already scaled keep mask (0 or 1/(1-rate)); NULL = inference
+ *   head_gamma/beta [O]        ln_output; non-NULL = also emit logits
+ *   out_caps     [B,S,O,D]     layer output (after LN and dropout); may be NULL in a
+ *                              stack call (library workspace is used)
+ *   out_logits   [B,S,O]       required iff head_gamma != NULL
+ */
+typedef struct srf_layer_desc {
+  const float* emb;
+  const float* W;
+  const float* bias;
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* dropout_mask;
+  const float* head_gamma;
+  const float* head_beta;
+  float* out_caps;
+  float* out_logits;
+  int32_t B, S;        /* utterances, routing frames per utterance                    */
+  int32_t H, d;        /* input capsules per frame, input capsule dim                 */
+  int32_t O, D;        /* output capsules, output capsule dim                         */
+  int32_t lpad, rpad;  /* --model-caps-window-{lpad,rpad}                             */
+  int32_t iters;       /* --model-caps-iter (ITER)                                    */
+  int32_t sdr;         /* --model-caps-context: 1 = SDR (sequential), 0 = DR          */
+  int32_t mask_class0; /* 1 on the last layer: -1e9 on output capsule 0 (naive:174,219) */
+  int32_t uhat_mode;   /* SRF_UHAT_*                                                  */
+  float ln_eps;        /* Keras LayerNormalization default 1e-3                       */
+  float length_eps;    /* 1e-7 (naive:256); the einsum variant uses 1e-9 (einsum:238)  */
+  uint64_t weights_version; /* != 0: packed weights cached in the handle under this tag
+                               until W/bias pointers, shapes or the tag change;
+                               0 = repack on every call                              */
+} srf_layer_desc;
+
+/* library version (SRF_B200_VERSION of the built .so) */
+int srf_version(void);
+
+/* create / destroy the per-device workspace handle (host pointers) */
+int srf_create(int device, srf_handle** out);
+int srf_destroy(srf_handle* h);
+
+/* last error message of this handle (host string, valid until the next call); h may be
+ * NULL for errors of srf_create */
+const char* srf_last_error(const srf_handle* h);
+
+/* one routing layer, forward.  Replaces naive:145-191 (+193 when the head is requested). */
+int srf_route_layer_fwd(srf_handle* h, const srf_layer_desc* layer, void* stream);
+
+/*
+ * the whole routing stack, forward: `for i in range(self.enc_num)` of naive:145-191
+ * plus the head naive:193.  layers[0].emb is the primary-capsule tensor; for n > 0 a NULL
+ * layers[n].emb means "the previous layer's output"; NULL out_caps = library workspace.
+ * The B,S of all layers must agree and layers[n].H,d must equal layers[n-1].O,D.
+ */
+int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, int32_t n_layers,
+                        void* stream);
+
+/* number of kernels this library has launched through the handle since creation
+ * (bench.py's gpu_launches claim is read from here) */
+int64_t srf_launch_count(const srf_handle* h);
+
+/* name of the u_hat / routing kernel variant the last layer call dispatched to (host string) */
+const char* srf_last_kernel(const srf_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRF_B200_H_ */

@@ -1,0 +1,11 @@
+"""srf_b200: B200-native (sm_100a) capsule-routing hot path of sephiroce/srf.
+
+Public surface:
+    SequenceRouter   -- drop-in for tfsr.model.sequence_router_naive.SequenceRouter
+    RoutingStack     -- the routing stack alone (primary capsules -> CTC logits)
+    routing          -- tensor-level wrappers of the C-ABI (include/srf_b200.h)
+"""
+from . import _lib, routing  # noqa: F401
+from .sequence_router import RoutingStack, layer_shapes  # noqa: F401
+
+__all__ = ["routing", "RoutingStack", "layer_shapes"]

@@ -1,0 +1,40 @@
+// routing_kernels.h -- internal interface between the C-ABI (capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#ifndef SRF_NW
+#define SRF_NW 8  // warps per CTA of the fused FP32 layer kernel
+#endif
+
+namespace srf {
+
+struct RouteParams {
+  const float* emb;           // [B,S,H,d]
+  const float* Wp;            // packed weights (see pack_weights_kernel)
+  const float* Bp;            // packed bias
+  const float* ln_gamma;      // [O*D] or null
+  const float* ln_beta;
+  const float* dropout_mask;  // [B,S,O,D] or null
+  const float* head_gamma;    // [O] or null
+  const float* head_beta;
+  float* out_caps;            // [B,S,O,D] or null
+  float* out_logits;          // [B,S,O] or null
+  int B, S, H, d, O, D, I;
+  int lpad, iters, sdr, mask0;
+  int C;        // cluster size (CTAs that split the input capsules of one chain group)
+  int Ic;       // input capsules per CTA = ceil(I / C)
+  int nchains;  // SDR: B, DR: B*S
+  int nsteps;   // SDR: S, DR: 1
+  float ln_eps, length_eps;
+};
+
+void launch_pack_weights(const float* W, const float* bias, float* Wp, float* Bp, int I, int O,
+                         int D, int d, int T, int OP, cudaStream_t stream);
+
+size_t route_layer_smem_bytes(int T, int OPL, int F, int NW, int Ic);
+int route_layer_max_F(int T, int OPL);
+cudaError_t launch_route_layer(const RouteParams& p, int T, int OPL, int F, int groups,
+                               size_t smem_bytes, cudaStream_t stream);
+
+}  // namespace srf

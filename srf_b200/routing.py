@@ -1,0 +1,202 @@
+"""Host side of the routing hot path: tensors in (torch or anything speaking DLPack), C-ABI
+call, tensors out.  torch is used only for device memory and streams.
+
+Reference semantics: tfsr/model/sequence_router_naive.py:145-193 (see include/srf_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+LN_EPS = 1e-3       # Keras LayerNormalization default (naive:104-107)
+LENGTH_EPS = 1e-7   # naive:256
+
+
+def as_device_tensor(x, device: Optional[torch.device] = None) -> torch.Tensor:
+  """Borrow `x` as a contiguous float32 CUDA tensor.  Accepts torch tensors and any object
+  implementing the DLPack protocol (e.g. tf.experimental.dlpack / EagerTensor.__dlpack__)."""
+  if not isinstance(x, torch.Tensor):
+    if hasattr(x, "__dlpack__"):
+      x = torch.from_dlpack(x)
+    else:
+      raise TypeError("expected a torch.Tensor or a DLPack-capable tensor, got %r" % type(x))
+  if not x.is_cuda:
+    if device is None:
+      raise ValueError("srf_b200 routing needs CUDA tensors (there is no CPU path)")
+    x = x.to(device, non_blocking=True)
+  if x.dtype != torch.float32:
+    raise ValueError("srf_b200 routing needs float32 tensors, got %s" % x.dtype)
+  return x.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Handle:
+  """Per-device workspace handle (srf_create / srf_destroy)."""
+
+  def __init__(self, device=None):
+    self.lib = _lib.load()
+    if not torch.cuda.is_available():
+      raise RuntimeError("srf_b200: no CUDA device visible; the routing path has no CPU fallback")
+    self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    h = ctypes.c_void_p()
+    rc = self.lib.srf_create(self.device.index or 0, ctypes.byref(h))
+    _lib.check(self.lib, None, rc, "srf_create")
+    self._h = h
+
+  def close(self):
+    if getattr(self, "_h", None):
+      self.lib.srf_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  @property
+  def launches(self) -> int:
+    return int(self.lib.srf_launch_count(self._h))
+
+  @property
+  def last_kernel(self) -> str:
+    return self.lib.srf_last_kernel(self._h).decode()
+
+
+_handles = {}
+
+
+def default_handle(device=None) -> Handle:
+  dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+  key = dev.index or 0
+  if key not in _handles:
+    _handles[key] = Handle(dev)
+  return _handles[key]
+
+
+@dataclass
+class LayerArgs:
+  """Python mirror of srf_layer_desc; tensors are kept alive until the call returns."""
+  W: torch.Tensor
+  bias: torch.Tensor
+  lpad: int
+  rpad: int
+  iters: int
+  sdr: bool
+  mask_class0: bool
+  ln_gamma: Optional[torch.Tensor] = None
+  ln_beta: Optional[torch.Tensor] = None
+  dropout_mask: Optional[torch.Tensor] = None
+  head_gamma: Optional[torch.Tensor] = None
+  head_beta: Optional[torch.Tensor] = None
+  uhat_mode: str = "fp32"
+  ln_eps: float = LN_EPS
+  length_eps: float = LENGTH_EPS
+  weights_version: int = 0
+  keep: list = field(default_factory=list)
+
+
+def _fill_desc(desc: _lib.LayerDesc, a: LayerArgs, emb, B, S, H, d, out_caps, out_logits):
+  I, O, D, d_w = a.W.shape
+  window = a.lpad + a.rpad + 1
+  if I != window * H or d_w != d:
+    raise ValueError("W shape %s does not match window*H=%d, d=%d" % (tuple(a.W.shape), window * H, d))
+  if tuple(a.bias.shape) != (I, O, D):
+    raise ValueError("bias shape %s != %s" % (tuple(a.bias.shape), (I, O, D)))
+  for name, t, n in (("ln_gamma", a.ln_gamma, O * D), ("ln_beta", a.ln_beta, O * D),
+                     ("head_gamma", a.head_gamma, O), ("head_beta", a.head_beta, O)):
+    if t is not None and t.numel() != n:
+      raise ValueError("%s has %d elements, expected %d" % (name, t.numel(), n))
+  if a.dropout_mask is not None and a.dropout_mask.numel() != B * S * O * D:
+    raise ValueError("dropout_mask has %d elements, expected %d" % (a.dropout_mask.numel(), B * S * O * D))
+  if a.uhat_mode not in _lib.UHAT_MODES:
+    raise ValueError("unknown uhat_mode %r" % (a.uhat_mode,))
+  desc.emb = _ptr(emb)
+  desc.W, desc.bias = _ptr(a.W), _ptr(a.bias)
+  desc.ln_gamma, desc.ln_beta = _ptr(a.ln_gamma), _ptr(a.ln_beta)
+  desc.dropout_mask = _ptr(a.dropout_mask)
+  desc.head_gamma, desc.head_beta = _ptr(a.head_gamma), _ptr(a.head_beta)
+  desc.out_caps, desc.out_logits = _ptr(out_caps), _ptr(out_logits)
+  desc.B, desc.S, desc.H, desc.d, desc.O, desc.D = B, S, H, d, O, D
+  desc.lpad, desc.rpad, desc.iters = a.lpad, a.rpad, a.iters
+  desc.sdr, desc.mask_class0 = int(bool(a.sdr)), int(bool(a.mask_class0))
+  desc.uhat_mode = _lib.UHAT_MODES[a.uhat_mode]
+  desc.ln_eps, desc.length_eps = a.ln_eps, a.length_eps
+  desc.weights_version = a.weights_version
+  return O, D
+
+
+def _prep(a: LayerArgs, dev):
+  a.W = as_device_tensor(a.W, dev)
+  a.bias = as_device_tensor(a.bias, dev)
+  for n in ("ln_gamma", "ln_beta", "dropout_mask", "head_gamma", "head_beta"):
+    t = getattr(a, n)
+    if t is not None:
+      setattr(a, n, as_device_tensor(t, dev))
+
+
+def route_layer_fwd(emb, args: LayerArgs, handle: Optional[Handle] = None):
+  """One routing layer (srf_route_layer_fwd).  emb [B,S,H,d] -> (capsules [B,S,O,D],
+  logits [B,S,O] or None)."""
+  emb = as_device_tensor(emb)
+  if emb.dim() != 4:
+    raise ValueError("emb must be [B,S,H,d], got %s" % (tuple(emb.shape),))
+  h = handle or default_handle(emb.device)
+  _prep(args, emb.device)
+  B, S, H, d = emb.shape
+  O, D = args.W.shape[1], args.W.shape[2]
+  out_caps = torch.empty((B, S, O, D), dtype=torch.float32, device=emb.device)
+  out_logits = torch.empty((B, S, O), dtype=torch.float32, device=emb.device) \
+      if args.head_gamma is not None else None
+  desc = _lib.LayerDesc()
+  _fill_desc(desc, args, emb, B, S, H, d, out_caps, out_logits)
+  stream = ctypes.c_void_p(torch.cuda.current_stream(emb.device).cuda_stream)
+  rc = h.lib.srf_route_layer_fwd(h._h, ctypes.byref(desc), stream)
+  _lib.check(h.lib, h._h, rc, "srf_route_layer_fwd")
+  return out_caps, out_logits
+
+
+def route_stack_fwd(emb, layers: Sequence[LayerArgs], handle: Optional[Handle] = None,
+                    return_capsules: bool = False, out_logits: Optional[torch.Tensor] = None):
+  """The whole routing stack (srf_route_stack_fwd): emb [B,S,PH,PD] -> logits [B,S,class_n].
+  The last layer must carry head_gamma/head_beta.  With return_capsules every layer's
+  output is also returned (used by the parity tests)."""
+  emb = as_device_tensor(emb)
+  if emb.dim() != 4:
+    raise ValueError("emb must be [B,S,H,d], got %s" % (tuple(emb.shape),))
+  if not layers:
+    raise ValueError("no layers")
+  h = handle or default_handle(emb.device)
+  B, S, H, d = emb.shape
+  n = len(layers)
+  descs = (_lib.LayerDesc * n)()
+  caps: List[torch.Tensor] = []
+  if layers[-1].head_gamma is None:
+    raise ValueError("the last layer must carry the head (head_gamma/head_beta)")
+  O_last = layers[-1].W.shape[1]
+  if out_logits is None:
+    out_logits = torch.empty((B, S, O_last), dtype=torch.float32, device=emb.device)
+  for i, a in enumerate(layers):
+    _prep(a, emb.device)
+    O, D = a.W.shape[1], a.W.shape[2]
+    oc = torch.empty((B, S, O, D), dtype=torch.float32, device=emb.device) if return_capsules else None
+    if oc is not None:
+      caps.append(oc)
+    _fill_desc(descs[i], a, emb if i == 0 else None, B, S, H, d, oc,
+               out_logits if i == n - 1 else None)
+    H, d = O, D
+  stream = ctypes.c_void_p(torch.cuda.current_stream(emb.device).cuda_stream)
+  rc = h.lib.srf_route_stack_fwd(h._h, descs, n, stream)
+  _lib.check(h.lib, h._h, rc, "srf_route_stack_fwd")
+  if return_capsules:
+    return out_logits, caps
+  return out_logits

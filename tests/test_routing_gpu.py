@@ -1,0 +1,207 @@
+"""Parity of the CUDA routing path (through the C-ABI) with the CPU oracle.
+
+Tolerance (BASELINE.json north_star): capsule outputs within 1e-4 relative for fp32
+routing; greedy-CTC label sequences identical."""
+import pytest
+import torch
+
+from oracle import srf_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_FP32 = 1e-4
+
+
+def rel_err(a: torch.Tensor, ref: torch.Tensor) -> float:
+  ref = ref.double()
+  return ((a.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def _mk_layer(B, S, H, d, O, D, window, seed):
+  g = torch.Generator().manual_seed(seed)
+  emb = torch.randn(B, S, H, d, generator=g)
+  W = torch.randn(window * H, O, D, d, generator=g) * 0.1
+  bias = torch.randn(window * H, O, D, generator=g) * 0.1
+  return emb, W, bias
+
+
+def _run_layer(emb, W, bias, lpad, rpad, iters, sdr, last, **kw):
+  from srf_b200 import routing
+  args = routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=lpad, rpad=rpad, iters=iters,
+                           sdr=sdr, mask_class0=last, **kw)
+  caps, logits = routing.route_layer_fwd(emb.cuda(), args)
+  torch.cuda.synchronize()
+  return caps, logits
+
+
+LAYER_CASES = [
+    # B, S, H, d, O, D, lpad, rpad
+    (2, 9, 6, 8, 5, 8, 1, 1),
+    (3, 5, 60, 8, 30, 8, 1, 1),      # TIMIT layer 0
+    (2, 6, 30, 8, 63, 8, 1, 1),      # TIMIT last layer (O = 63 -> 2 capsules per lane)
+    (2, 5, 30, 8, 30, 8, 3, 3),      # cfg-2 window 7
+    (2, 7, 60, 20, 30, 20, 2, 2),    # WSJ layer 0
+    (1, 4, 30, 20, 32, 20, 2, 2),    # WSJ last layer
+    (2, 5, 7, 16, 9, 16, 0, 0),      # window 1
+    (1, 6, 5, 32, 6, 32, 4, 4),      # DIM 32, window 9
+    (2, 5, 7, 5, 9, 7, 1, 0),        # odd dims (padded inside the kernel), asymmetric window
+    (1, 1, 4, 8, 3, 8, 2, 2),        # a single frame, window wider than the sequence
+    (2, 4, 9, 8, 100, 8, 0, 1),      # 100 output capsules (4 per lane)
+]
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+@pytest.mark.parametrize("sdr", [True, False])
+@pytest.mark.parametrize("iters", [1, 3])
+@pytest.mark.parametrize("last", [False, True])
+def test_single_layer_matches_oracle(case, sdr, iters, last):
+  B, S, H, d, O, D, lpad, rpad = case
+  emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=hash(case) % 1000)
+  ref = o.route_layer(emb.double(), W.double(), bias.double(), lpad, rpad, iters, sdr, last)
+  caps, _ = _run_layer(emb, W, bias, lpad, rpad, iters, sdr, last)
+  assert caps.shape == (B, S, O, D)
+  assert rel_err(caps, ref) < REL_TOL_FP32
+  if last:
+    assert torch.count_nonzero(caps[:, :, 0]) == 0   # class 0 exactly zero (naive:219-224)
+
+
+@pytest.mark.parametrize("iters", [2, 5])
+def test_more_iterations(iters):
+  emb, W, bias = _mk_layer(2, 6, 10, 8, 12, 8, 3, seed=7)
+  for sdr in (True, False):
+    ref = o.route_layer(emb.double(), W.double(), bias.double(), 1, 1, iters, sdr, False)
+    caps, _ = _run_layer(emb, W, bias, 1, 1, iters, sdr, False)
+    assert rel_err(caps, ref) < REL_TOL_FP32
+
+
+def test_layernorm_dropout_and_head_fused():
+  B, S, H, d, O, D = 2, 6, 8, 8, 11, 8
+  emb, W, bias = _mk_layer(B, S, H, d, O, D, 3, seed=3)
+  g = torch.Generator().manual_seed(5)
+  gam, bet = 1 + 0.2 * torch.randn(O * D, generator=g), 0.1 * torch.randn(O * D, generator=g)
+  hg, hb = 1 + 0.2 * torch.randn(O, generator=g), 0.1 * torch.randn(O, generator=g)
+  mask = (torch.rand(B, S, O, D, generator=g) < 0.9).float() / 0.9
+  for sdr in (True, False):
+    v = o.route_layer(emb.double(), W.double(), bias.double(), 1, 1, 2, sdr, True)
+    y = o.layer_norm(v.reshape(B, S, O * D), gam.double(), bet.double()).reshape(B, S, O, D) * mask.double()
+    lg = o.layer_norm(o.length(y), hg.double(), hb.double())
+    caps, logits = _run_layer(emb, W, bias, 1, 1, 2, sdr, True, ln_gamma=gam.cuda(),
+                              ln_beta=bet.cuda(), dropout_mask=mask.cuda(),
+                              head_gamma=hg.cuda(), head_beta=hb.cuda())
+    assert rel_err(caps, y) < REL_TOL_FP32
+    assert rel_err(logits, lg) < REL_TOL_FP32
+
+
+STACK_CASES = [
+    # name, enc_num, PH, CH, class_n, DIM, lpad, rpad, iters, sdr, B, S
+    ("timit_sdr_i1", 7, 60, 30, 63, 8, 1, 1, 1, True, 2, 16),
+    ("timit_dr_i3_w7", 7, 60, 30, 63, 8, 3, 3, 3, False, 2, 12),
+    ("wsj_sdr_i1", 10, 60, 30, 32, 20, 2, 2, 1, True, 2, 10),
+    ("one_layer", 1, 12, 6, 9, 8, 1, 1, 2, True, 3, 5),
+    ("two_layer_dr", 2, 12, 6, 9, 16, 0, 2, 2, False, 3, 5),
+]
+
+
+@pytest.mark.parametrize("case", STACK_CASES, ids=[c[0] for c in STACK_CASES])
+def test_full_stack_matches_oracle_and_greedy_ctc(case):
+  from srf_b200 import RoutingStack
+  _, L, PH, CH, class_n, DIM, lpad, rpad, iters, sdr, B, S = case
+  window = lpad + rpad + 1
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, window)
+  p32 = o.init_params(shapes, class_n, seed=11, random_ln=True)
+  emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(12))
+  ref_logits, ref_caps = o.route_stack(emb.double(), p32.to(torch.float64), lpad, rpad, iters, sdr,
+                                       return_capsules=True)
+  stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, sdr, seed=0)
+  stack.load_oracle_params(p32)
+  logits, caps = stack.forward(emb.cuda(), return_capsules=True)
+  torch.cuda.synchronize()
+  for i, (c, r) in enumerate(zip(caps[:-1], ref_caps[:-1])):
+    assert rel_err(c, r) < REL_TOL_FP32, "layer %d" % i
+  assert rel_err(logits, ref_logits) < REL_TOL_FP32
+  lens = [S] + [max(1, S - 3)] * (B - 1)
+  assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(ref_logits, lens)
+  # workspace path (no per-layer outputs requested) gives the same logits
+  logits2 = stack.forward(emb.cuda())
+  torch.cuda.synchronize()
+  assert torch.equal(logits, logits2)
+
+
+def test_batch_rows_are_independent_and_deterministic():
+  from srf_b200 import RoutingStack
+  stack = RoutingStack(3, 12, 6, 9, 8, 8, 8, 1, 1, 1, True, seed=3)
+  emb = torch.randn(5, 7, 12, 8, generator=torch.Generator().manual_seed(4)).cuda()
+  a = stack.forward(emb)
+  b = stack.forward(emb[[4, 2, 0, 1, 3]].contiguous())
+  c = stack.forward(emb)
+  torch.cuda.synchronize()
+  assert torch.equal(a, c)
+  assert rel_err(b, a[[4, 2, 0, 1, 3]].cpu()) < 1e-6
+
+
+def test_cluster_split_is_consistent(monkeypatch):
+  """Splitting the input capsules over a thread-block cluster only re-associates the sum
+  over i."""
+  from srf_b200 import routing
+  emb, W, bias = _mk_layer(3, 8, 60, 8, 30, 8, 3, seed=21)
+  ref = o.route_layer(emb.double(), W.double(), bias.double(), 1, 1, 2, True, False)
+  outs = []
+  for C in ("1", "2", "4", "8"):
+    monkeypatch.setenv("SRF_FORCE_C", C)
+    h = routing.Handle()
+    args = routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=1, rpad=1, iters=2, sdr=True,
+                             mask_class0=False)
+    caps, _ = routing.route_layer_fwd(emb.cuda(), args, handle=h)
+    torch.cuda.synchronize()
+    assert "C=%s " % C in h.last_kernel
+    assert rel_err(caps, ref) < REL_TOL_FP32
+    outs.append(caps)
+    h.close()
+  for x in outs[1:]:
+    assert rel_err(x, outs[0].cpu()) < 1e-5
+
+
+def test_empty_batch_and_errors():
+  from srf_b200 import routing
+  emb, W, bias = _mk_layer(2, 4, 6, 8, 5, 8, 3, seed=1)
+  args = routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=1, rpad=1, iters=1, sdr=True,
+                           mask_class0=False)
+  caps, _ = routing.route_layer_fwd(emb[:0].cuda(), args)
+  assert caps.shape == (0, 4, 5, 8)
+  with pytest.raises(ValueError):   # window does not match W
+    routing.route_layer_fwd(emb.cuda(), routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=2, rpad=1,
+                                                          iters=1, sdr=True, mask_class0=False))
+  with pytest.raises(ValueError):   # iters < 1
+    routing.route_layer_fwd(emb.cuda(), routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=1, rpad=1,
+                                                          iters=0, sdr=True, mask_class0=False))
+  with pytest.raises(ValueError):   # no CPU path
+    routing.route_layer_fwd(emb, args)
+  with pytest.raises(ValueError):   # dtype
+    routing.route_layer_fwd(emb.cuda().double(), args)
+  with pytest.raises(ValueError):   # capsule dim > 32
+    e2, W2, b2 = _mk_layer(1, 2, 3, 40, 4, 40, 1, seed=2)
+    routing.route_layer_fwd(e2.cuda(), routing.LayerArgs(W=W2.cuda(), bias=b2.cuda(), lpad=0, rpad=0,
+                                                         iters=1, sdr=True, mask_class0=False))
+
+
+def test_dlpack_interchange():
+  """Any DLPack producer is accepted (the reference's tensors are tf.Tensors; numpy-on-host
+  is rejected because there is no CPU path)."""
+  from srf_b200 import routing
+
+  class Foreign:
+    def __init__(self, t):
+      self.t = t
+
+    def __dlpack__(self, stream=None):
+      return self.t.__dlpack__()
+
+    def __dlpack_device__(self):
+      return self.t.__dlpack_device__()
+
+  emb, W, bias = _mk_layer(2, 4, 6, 8, 5, 8, 3, seed=1)
+  args = routing.LayerArgs(W=Foreign(W.cuda()), bias=Foreign(bias.cuda()), lpad=1, rpad=1, iters=1,
+                           sdr=False, mask_class0=False)
+  caps, _ = routing.route_layer_fwd(Foreign(emb.cuda()), args)
+  ref = o.route_layer(emb.double(), W.double(), bias.double(), 1, 1, 1, False, False)
+  assert rel_err(caps, ref) < REL_TOL_FP32

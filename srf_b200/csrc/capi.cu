@@ -208,9 +208,9 @@ static int pow2_floor(int v) {
 }
 
 static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t stream) {
+  if (L && (L->B == 0 || L->S == 0)) return 0;  // empty batch: nothing to do
   int rc = validate_layer(h, L);
   if (rc) return rc;
-  if (L->B == 0 || L->S == 0) return 0;  // empty batch: nothing to do
   if (!L->out_caps && !L->out_logits) return fail(h, -1, "no output requested");
 
   const int window = L->lpad + L->rpad + 1;

@@ -205,3 +205,28 @@ def test_dlpack_interchange():
   caps, _ = routing.route_layer_fwd(Foreign(emb.cuda()), args)
   ref = o.route_layer(emb.double(), W.double(), bias.double(), 1, 1, 1, False, False)
   assert rel_err(caps, ref) < REL_TOL_FP32
+
+
+def _golden_names():
+  from tests import golden_util as gu
+  return gu.golden_names()
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_cuda_path_matches_reference_goldens(name):
+  """CUDA routing stack vs the vectors produced by the reference's own source file."""
+  from srf_b200 import RoutingStack
+  from tests import golden_util as gu
+  g = gu.load(name)
+  k = g["knobs"]
+  stack = RoutingStack(k["L"], k["PH"], k["CH"], k["class_n"], k["DIM"], k["DIM"], k["DIM"],
+                       k["lpad"], k["rpad"], k["iters"], k["sdr"], seed=0)
+  stack.load_oracle_params(g["params"])
+  masks = None if g["masks"] is None else [m.float().cuda() for m in g["masks"]]
+  logits, caps = stack.forward(g["emb"].float().cuda(), dropout_masks=masks, return_capsules=True)
+  torch.cuda.synchronize()
+  for i, (c, r) in enumerate(zip(caps[:-1], g["caps"][:-1])):
+    assert rel_err(c, r) < REL_TOL_FP32, "layer %d" % i
+  assert rel_err(logits, g["logits"]) < REL_TOL_FP32
+  lens = [int(n) // 4 for n in g["input_lengths"]]
+  assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(g["logits"], lens)

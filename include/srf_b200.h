@@ -103,6 +103,14 @@ int srf_route_layer_fwd(srf_handle* h, const srf_layer_desc* layer, void* stream
 int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, int32_t n_layers,
                         void* stream);
 
+/*
+ * prediction vectors alone: window gather + u_hat = W.x + bias (naive:150-159) for every frame,
+ * written in the reference's [B,S,I,O,D] layout (naive:158), fp32.  Uses emb, W, bias, B,S,H,d,
+ * O,D, lpad, rpad and uhat_mode of the descriptor: SRF_UHAT_TF32 / SRF_UHAT_BF16 run the tcgen05
+ * GEMM (u_hat kept in fp32 / bf16 before the copy-out).  Requires d % 4 == 0.
+ */
+int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* layer, float* out_uhat, void* stream);
+
 /* number of kernels this library has launched through the handle since creation
  * (bench.py's gpu_launches claim is read from here) */
 int64_t srf_launch_count(const srf_handle* h);

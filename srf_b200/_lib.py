@@ -14,7 +14,7 @@ UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF1
 
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",
-           "srf_route_stack_fwd", "srf_launch_count", "srf_last_kernel")
+           "srf_route_stack_fwd", "srf_uhat_fwd", "srf_launch_count", "srf_last_kernel")
 
 
 class LayerDesc(Structure):
@@ -54,6 +54,8 @@ def load() -> ctypes.CDLL:
   lib.srf_route_layer_fwd.restype = c_int
   lib.srf_route_stack_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_int32, c_void_p]
   lib.srf_route_stack_fwd.restype = c_int
+  lib.srf_uhat_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_void_p, c_void_p]
+  lib.srf_uhat_fwd.restype = c_int
   lib.srf_launch_count.argtypes = [c_void_p]
   lib.srf_launch_count.restype = c_int64
   lib.srf_last_kernel.argtypes = [c_void_p]

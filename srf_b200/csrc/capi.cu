@@ -1,6 +1,7 @@
 // capi.cu -- the C-ABI of include/srf_b200.h: handle, argument validation, packed-weight
 // cache, kernel-variant dispatch and the per-layer stack driver.  No torch types here.
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -38,6 +39,11 @@ struct srf_handle {
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
   int force_F = 0, force_C = 0;
+  // tensor-core path
+  std::vector<PackedWeights> packed_mma;
+  void* ubuf = nullptr;  // materialised u_hat of one layer
+  size_t ubuf_bytes = 0;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled
 };
 
 static std::string g_create_error;
@@ -108,6 +114,10 @@ extern "C" int srf_destroy(srf_handle* h) {
   for (auto& pw : h->packed) {
     if (pw.Wp) cudaFree(pw.Wp);
   }
+  for (auto& pw : h->packed_mma) {
+    if (pw.Wp) cudaFree(pw.Wp);
+  }
+  if (h->ubuf) cudaFree(h->ubuf);
   for (int i = 0; i < 2; ++i)
     if (h->ws[i]) cudaFree(h->ws[i]);
   delete h;
@@ -198,6 +208,187 @@ static int get_packed(srf_handle* h, const srf_layer_desc* L, int I, int T, int 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, "pack_weights launch");
   *out = hit;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// tensor-core u_hat (uhat_gemm.cu): packed MMA weights, TMA tensor map over emb, launch
+// ---------------------------------------------------------------------------------------
+namespace {
+struct UhatGeom {
+  int I, T, OPL, MT, KC, NB, NS, NBT, NST, Bpad;
+  bool bf16;
+  size_t bytes;
+};
+}  // namespace
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
+  if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_BF16)
+    return fail(h, -4, "tensor-core u_hat needs uhat_mode TF32 or BF16");
+  if (L->d % 4 != 0)
+    return fail(h, -3, "tensor-core u_hat needs d %% 4 == 0 (got d=%d); use SRF_UHAT_FP32", L->d);
+  if ((reinterpret_cast<uintptr_t>(L->emb) & 15) != 0)
+    return fail(h, -3, "tensor-core u_hat needs a 16-byte aligned emb pointer");
+  const int window = L->lpad + L->rpad + 1;
+  g->I = window * L->H;
+  g->T = ((L->D + 3) / 4) * 4;
+  g->OPL = (L->O + 31) / 32;
+  g->MT = g->OPL * (g->T / 4);
+  g->KC = 2 * ((L->d + 7) / 8);
+  g->Bpad = (L->B + 1) & ~1;
+  int nb = 2;
+  while (nb < 64 && nb < g->Bpad) nb *= 2;
+  g->NB = nb;
+  g->NS = 64 / nb;
+  g->NBT = (L->B + g->NB - 1) / g->NB;
+  g->NST = (L->S + g->NS - 1) / g->NS;
+  g->bf16 = L->uhat_mode == SRF_UHAT_BF16;
+  g->bytes = (size_t)L->S * (g->Bpad / 2) * g->I * g->MT * 128 * 2 * (g->bf16 ? 2 : 4);
+  const size_t smem = srf::uhat_gemm_smem_bytes(g->MT, g->KC);
+  if (smem > (size_t)h->max_smem)
+    return fail(h, -3, "u_hat GEMM tile does not fit in shared memory (O=%d, D=%d, d=%d)", L->O,
+                L->D, L->d);
+  return 0;
+}
+
+static int get_packed_mma(srf_handle* h, const srf_layer_desc* L, const UhatGeom& g,
+                          cudaStream_t stream, const PackedWeights** out) {
+  PackedWeights* hit = nullptr;
+  for (auto& pw : h->packed_mma)
+    if (pw.W == L->W && pw.bias == L->bias) {
+      hit = &pw;
+      break;
+    }
+  const size_t nW = (size_t)g.I * g.MT * g.KC * 512, nB = (size_t)g.I * g.MT * 128;
+  const size_t bytes = (nW + nB) * sizeof(float);
+  const bool same = hit && hit->I == g.I && hit->O == L->O && hit->D == L->D && hit->d == L->d;
+  if (same && L->weights_version != 0 && hit->version == L->weights_version) {
+    *out = hit;
+    return 0;
+  }
+  if (!hit) {
+    if (h->packed_mma.size() >= 64) {
+      for (auto& pw : h->packed_mma)
+        if (pw.Wp) cudaFreeAsync(pw.Wp, stream);
+      h->packed_mma.clear();
+    }
+    h->packed_mma.emplace_back();
+    hit = &h->packed_mma.back();
+  }
+  if (hit->bytes < bytes) {
+    if (hit->Wp) cudaFreeAsync(hit->Wp, stream);
+    hit->Wp = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&hit->Wp, bytes, stream);
+    if (e != cudaSuccess) {
+      hit->bytes = 0;
+      return cuda_fail(h, e, "packed MMA weight allocation");
+    }
+    hit->bytes = bytes;
+  }
+  hit->Bp = hit->Wp + nW;
+  hit->W = L->W;
+  hit->bias = L->bias;
+  hit->I = g.I;
+  hit->O = L->O;
+  hit->D = L->D;
+  hit->d = L->d;
+  hit->version = L->weights_version;
+  srf::launch_pack_weights_mma(L->W, L->bias, hit->Wp, hit->Bp, g.I, L->O, L->D, L->d, g.T, g.OPL,
+                               g.KC, stream);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, "pack_weights_mma launch");
+  *out = hit;
+  return 0;
+}
+
+// runs the GEMM; on return h->ubuf holds u_hat of this layer in the streaming layout
+static int compute_uhat(srf_handle* h, const srf_layer_desc* L, const UhatGeom& g,
+                        cudaStream_t stream) {
+  const PackedWeights* pw = nullptr;
+  int rc = get_packed_mma(h, L, g, stream, &pw);
+  if (rc) return rc;
+  if (h->ubuf_bytes < g.bytes) {
+    if (h->ubuf) cudaFreeAsync(h->ubuf, stream);
+    h->ubuf = nullptr;
+    h->ubuf_bytes = 0;
+    cudaError_t e = cudaMallocAsync(&h->ubuf, g.bytes, stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "u_hat buffer allocation");
+    h->ubuf_bytes = g.bytes;
+  }
+  if (!h->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+      return fail(h, e != cudaSuccess ? (int)e : 999, "cuTensorMapEncodeTiled is not available");
+    h->encode_tiled = fn;
+  }
+  // emb[B,S,H,d] viewed as 5-D (l_in=4, b, s, h, l4=d/4); box (4, NB, NS, 1, KC) lands in
+  // shared memory as [K chunk][s][b][4 floats] = the canonical K-major UMMA operand layout.
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {4, (cuuint64_t)L->B, (cuuint64_t)L->S, (cuuint64_t)L->H,
+                              (cuuint64_t)(L->d / 4)};
+  const cuuint64_t gstr[4] = {(cuuint64_t)L->S * L->H * L->d * 4, (cuuint64_t)L->H * L->d * 4,
+                              (cuuint64_t)L->d * 4, 16};
+  const cuuint32_t box[5] = {4, (cuuint32_t)g.NB, (cuuint32_t)g.NS, 1, (cuuint32_t)g.KC};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = ((EncodeTiledFn)h->encode_tiled)(
+      &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(L->emb), gdim, gstr, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(h, 900 + (int)cr, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
+
+  srf::UhatParams p;
+  p.Wm = pw->Wp;
+  p.Bm = pw->Bp;
+  p.u = h->ubuf;
+  p.I = g.I;
+  p.MT = g.MT;
+  p.KC = g.KC;
+  p.B = L->B;
+  p.S = L->S;
+  p.H = L->H;
+  p.lpad = L->lpad;
+  p.NB = g.NB;
+  p.NS = g.NS;
+  p.NBT = g.NBT;
+  p.NST = g.NST;
+  p.Bpad = g.Bpad;
+  p.store_bf16 = g.bf16 ? 1 : 0;
+  p.items = (long long)g.I * g.NBT * g.NST;
+  cudaError_t e = srf::launch_uhat_gemm(tmap, p, h->num_sms, stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "uhat_gemm launch");
+  h->launches++;
+  return 0;
+}
+
+extern "C" int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* L, float* out_uhat, void* stream_) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (!L || !out_uhat) return fail(h, -1, "layer descriptor or output is NULL");
+  if (L->B == 0 || L->S == 0) return 0;
+  if (!L->emb || !L->W || !L->bias) return fail(h, -1, "emb, W and bias must be non-NULL");
+  if (L->H <= 0 || L->d <= 0 || L->O <= 0 || L->D <= 0 || L->lpad < 0 || L->rpad < 0)
+    return fail(h, -2, "bad shape");
+  if (L->O > 128 || L->D > 32 || L->d > 32) return fail(h, -3, "O > 128 or capsule dim > 32");
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UhatGeom g;
+  int rc = uhat_geometry(h, L, &g);
+  if (rc) return rc;
+  rc = compute_uhat(h, L, g, stream);
+  if (rc) return rc;
+  srf::launch_unpack_uhat(h->ubuf, out_uhat, L->B, L->S, g.I, L->O, L->D, g.T, g.OPL, g.Bpad,
+                          g.bf16 ? 1 : 0, stream);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, "unpack_uhat launch");
+  h->last_kernel = "uhat_gemm_kernel(tcgen05 tf32)";
   return 0;
 }
 

@@ -29,6 +29,20 @@ struct RouteParams {
   float ln_eps, length_eps;
 };
 
+// u_hat GEMM (uhat_gemm.cu)
+struct UhatParams {
+  const float* Wm;  // packed A operand  [I][MT][KC][128][4]
+  const float* Bm;  // packed bias       [I][MT][128]
+  void* u;          // u_hat out         [S*Bpad/2 frame pairs][I][MT][128][2]  bf16 or fp32
+  int I, MT, KC;    // KC = 16-byte K chunks per row (2 per tf32 MMA)
+  int B, S, H, lpad;
+  int NB, NS;       // frame tile = NB utterances x NS time steps (NB*NS = 64)
+  int NBT, NST;     // number of tiles along b and s
+  int Bpad;         // B rounded up to even
+  int store_bf16;
+  long long items;  // I * NBT * NST
+};
+
 void launch_pack_weights(const float* W, const float* bias, float* Wp, float* Bp, int I, int O,
                          int D, int d, int T, int OP, cudaStream_t stream);
 
@@ -37,4 +51,18 @@ int route_layer_max_F(int T, int OPL);
 cudaError_t launch_route_layer(const RouteParams& p, int T, int OPL, int F, int groups,
                                size_t smem_bytes, cudaStream_t stream);
 
+void launch_pack_weights_mma(const float* W, const float* bias, float* Wm, float* Bm, int I, int O,
+                             int D, int d, int T, int OPL, int KC, cudaStream_t stream);
+size_t uhat_gemm_smem_bytes(int MT, int KC);
+void launch_unpack_uhat(const void* u, float* out, int B, int S, int I, int O, int D, int T, int OPL,
+                        int Bpad, int is_bf16, cudaStream_t stream);
+
 }  // namespace srf
+
+// needs <cuda.h> for CUtensorMap; declared separately so plain users of this header need not include it
+#ifdef CUDA_VERSION
+namespace srf {
+cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int num_sms,
+                             cudaStream_t stream);
+}
+#endif

@@ -200,3 +200,23 @@ def route_stack_fwd(emb, layers: Sequence[LayerArgs], handle: Optional[Handle] =
   if return_capsules:
     return out_logits, caps
   return out_logits
+
+
+def uhat_fwd(emb, W, bias, lpad: int, rpad: int, uhat_mode: str = "tf32",
+             handle: Optional[Handle] = None) -> torch.Tensor:
+  """Prediction vectors alone (srf_uhat_fwd, naive:150-159): [B,S,H,d] -> [B,S,I,O,D] fp32,
+  computed by the tcgen05 GEMM (tf32: fp32 u_hat storage, bf16: bf16 storage)."""
+  emb = as_device_tensor(emb)
+  h = handle or default_handle(emb.device)
+  a = LayerArgs(W=W, bias=bias, lpad=lpad, rpad=rpad, iters=1, sdr=False, mask_class0=False,
+                uhat_mode=uhat_mode)
+  _prep(a, emb.device)
+  B, S, H, d = emb.shape
+  I, O, D, _ = a.W.shape
+  out = torch.empty((B, S, I, O, D), dtype=torch.float32, device=emb.device)
+  desc = _lib.LayerDesc()
+  _fill_desc(desc, a, emb, B, S, H, d, None, None)
+  stream = ctypes.c_void_p(torch.cuda.current_stream(emb.device).cuda_stream)
+  rc = h.lib.srf_uhat_fwd(h._h, ctypes.byref(desc), ctypes.c_void_p(out.data_ptr()), stream)
+  _lib.check(h.lib, h._h, rc, "srf_uhat_fwd")
+  return out

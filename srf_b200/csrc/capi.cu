@@ -38,7 +38,7 @@ struct srf_handle {
   std::vector<PackedWeights> packed;
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
-  int force_F = 0, force_C = 0;
+  int force_F = 0, force_C = 0, no_stream = 0;
   // tensor-core path
   std::vector<PackedWeights> packed_mma;
   void* ubuf = nullptr;  // materialised u_hat of one layer
@@ -104,6 +104,7 @@ extern "C" int srf_create(int device, srf_handle** out) {
   h->max_smem = (int)prop.sharedMemPerBlockOptin;
   if (const char* s = getenv("SRF_FORCE_F")) h->force_F = atoi(s);
   if (const char* s = getenv("SRF_FORCE_C")) h->force_C = atoi(s);
+  if (const char* s = getenv("SRF_NO_STREAM")) h->no_stream = atoi(s);
   *out = h;
   return 0;
 }
@@ -149,9 +150,9 @@ static int validate_layer(srf_handle* h, const srf_layer_desc* L) {
   if ((L->head_gamma == nullptr) != (L->head_beta == nullptr))
     return fail(h, -1, "head_gamma and head_beta must both be given or both be NULL");
   if (L->head_gamma && !L->out_logits) return fail(h, -1, "head requested but out_logits is NULL");
-  if (L->uhat_mode != SRF_UHAT_FP32)
-    return fail(h, -4, "uhat_mode %d is not available in this build (only SRF_UHAT_FP32)",
-                L->uhat_mode);
+  if (L->uhat_mode != SRF_UHAT_FP32 && L->uhat_mode != SRF_UHAT_TF32 &&
+      L->uhat_mode != SRF_UHAT_BF16)
+    return fail(h, -4, "unknown uhat_mode %d", L->uhat_mode);
   if (L->O > 128) return fail(h, -3, "O = %d output capsules > 128 is not supported", L->O);
   if (L->D > 32 || L->d > 32)
     return fail(h, -3, "capsule dims D=%d, d=%d > 32 are not supported", L->D, L->d);
@@ -236,7 +237,7 @@ static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
     return fail(h, -3, "tensor-core u_hat needs a 16-byte aligned emb pointer");
   const int window = L->lpad + L->rpad + 1;
   g->I = window * L->H;
-  g->T = ((L->D + 3) / 4) * 4;
+  g->T = L->D <= 8 ? 8 : (L->D <= 16 ? 16 : (L->D <= 20 ? 20 : 32));  // = routing kernel's T
   g->OPL = (L->O + 31) / 32;
   g->MT = g->OPL * (g->T / 4);
   g->KC = 2 * ((L->d + 7) / 8);
@@ -406,36 +407,51 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
 
   const int window = L->lpad + L->rpad + 1;
   const int I = window * L->H;
-  const int m = L->D > L->d ? L->D : L->d;
-  const int T = m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 20 ? 20 : 32));
+  const int um = L->uhat_mode == SRF_UHAT_FP32 ? 0 : (L->uhat_mode == SRF_UHAT_BF16 ? 1 : 2);
   const int OPL = L->O <= 32 ? 1 : (L->O <= 64 ? 2 : 4);
   const int OP = 32 * OPL;
-
+  int T;
   const PackedWeights* pw = nullptr;
-  rc = get_packed(h, L, I, T, OP, stream, &pw);
-  if (rc) return rc;
+  UhatGeom g;
+  if (um == 0) {
+    const int m = L->D > L->d ? L->D : L->d;
+    T = m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 20 ? 20 : 32));
+    rc = get_packed(h, L, I, T, OP, stream, &pw);
+    if (rc) return rc;
+  } else {
+    // tensor-core path: u_hat of the whole layer by the tcgen05 GEMM, then stream it
+    rc = uhat_geometry(h, L, &g);
+    if (rc) return rc;
+    T = g.T;
+    if ((T == 16 && OPL > 2) || (T == 20 && OPL > 2) || (T == 32 && OPL > 1))
+      return fail(h, -3, "tensor-core path: O=%d with D=%d is not instantiated", L->O, L->D);
+    rc = compute_uhat(h, L, g, stream);
+    if (rc) return rc;
+  }
 
-  const long long nchains = L->sdr ? L->B : (long long)L->B * L->S;
+  const int halfB = (L->B + 1) / 2;
+  long long nchains = L->sdr ? L->B : (long long)L->B * L->S;
+  if (um != 0 && !L->sdr) nchains = 2LL * halfB * L->S;
   if (nchains > (1LL << 30)) return fail(h, -2, "too many frames");
   int F = srf::route_layer_max_F(T, OPL);
   while (F > 1 && ((nchains + F - 1) / F) * 8 < h->num_sms) F /= 2;
   if (h->force_F > 0 && h->force_F <= srf::route_layer_max_F(T, OPL)) F = h->force_F;
+  if (um != 0) F = 2;
   int groups = (int)((nchains + F - 1) / F);
   int C = pow2_floor(h->num_sms / groups > 0 ? h->num_sms / groups : 1);
   if (C > 8) C = 8;
   if (h->force_C > 0) C = h->force_C;
-  while (C > 1 && (I + C - 1) / C < 1) C /= 2;
   if (C > I) C = pow2_floor(I);
   // shared-memory fit: widen the cluster, then narrow the chain group
   for (;;) {
     const int Ic = (I + C - 1) / C;
-    const size_t smem = srf::route_layer_smem_bytes(T, OPL, F, SRF_NW, Ic);
+    const size_t smem = srf::route_layer_smem_bytes(T, OPL, F, SRF_NW, Ic, um);
     if (smem <= (size_t)h->max_smem) break;
     if (C < 8 && C * 2 <= I) {
       C *= 2;
       continue;
     }
-    if (F > 1) {
+    if (F > 1 && um == 0) {
       F /= 2;
       groups = (int)((nchains + F - 1) / F);
       continue;
@@ -443,12 +459,12 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
     return fail(h, -3, "layer does not fit in shared memory (I=%d, T=%d, O=%d)", I, T, L->O);
   }
   const int Ic = (I + C - 1) / C;
-  const size_t smem = srf::route_layer_smem_bytes(T, OPL, F, SRF_NW, Ic);
+  const size_t smem = srf::route_layer_smem_bytes(T, OPL, F, SRF_NW, Ic, um);
 
   srf::RouteParams p;
   p.emb = L->emb;
-  p.Wp = pw->Wp;
-  p.Bp = pw->Bp;
+  p.Wp = pw ? pw->Wp : nullptr;
+  p.Bp = pw ? pw->Bp : nullptr;
   p.ln_gamma = L->ln_gamma;
   p.ln_beta = L->ln_beta;
   p.dropout_mask = L->dropout_mask;
@@ -473,16 +489,49 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
   p.nsteps = L->sdr ? L->S : 1;
   p.ln_eps = L->ln_eps;
   p.length_eps = L->length_eps;
+  p.u = um != 0 ? h->ubuf : nullptr;
+  p.halfB = halfB;
 
-  cudaError_t e = srf::launch_route_layer(p, T, OPL, F, groups, smem, stream);
+  p.nstage = 0;
+  if (um != 0 && !h->no_stream) {
+    // streaming kernel: TMA-fed ring + warp-specialised output; needs >= 2 ring stages
+    int Cs = C;
+    if (Cs * groups > h->num_sms) Cs = pow2_floor(h->num_sms / groups > 0 ? h->num_sms / groups : 1);
+    const size_t stage = srf::route_stream_stage_bytes(T, OPL, um == 1);
+    const size_t fixed = srf::route_stream_fixed_smem(T, OPL, Cs, 16);
+    if (fixed + 2 * stage <= (size_t)h->max_smem) {
+      int nstage = (int)(((size_t)h->max_smem - fixed) / stage);
+      if (nstage > 16) nstage = 16;
+      p.C = Cs;
+      p.Ic = (I + Cs - 1) / Cs;
+      p.nstage = nstage;
+      const size_t smem_s = fixed + (size_t)nstage * stage;
+      cudaError_t es = srf::launch_route_stream(p, T, OPL, um == 1, groups, smem_s, stream);
+      if (es != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(h, es, "route_stream launch");
+      }
+      h->launches++;
+      char nm[200];
+      snprintf(nm, sizeof(nm),
+               "uhat_gemm_kernel(tcgen05 tf32) + route_stream_kernel<T=%d,OPL=%d,NW=%d,%s> C=%d "
+               "groups=%d stages=%d smem=%zu",
+               T, OPL, SRF_NW, um == 1 ? "bf16" : "fp32", Cs, groups, nstage, smem_s);
+      h->last_kernel = nm;
+      return 0;
+    }
+  }
+
+  cudaError_t e = srf::launch_route_layer(p, T, OPL, F, groups, smem, um, stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return cuda_fail(h, e, "route_layer launch");
   }
   h->launches++;
-  char name[128];
-  snprintf(name, sizeof(name), "route_layer_kernel<T=%d,OPL=%d,F=%d,NW=%d> C=%d groups=%d smem=%zu",
-           T, OPL, F, SRF_NW, C, groups, smem);
+  char name[160];
+  snprintf(name, sizeof(name),
+           "%sroute_layer_kernel<T=%d,OPL=%d,F=%d,NW=%d,UM=%d> C=%d groups=%d smem=%zu",
+           um != 0 ? "uhat_gemm_kernel(tcgen05 tf32) + " : "", T, OPL, F, SRF_NW, um, C, groups, smem);
   h->last_kernel = name;
   return 0;
 }

@@ -90,8 +90,13 @@ void launch_pack_weights(const float* W, const float* bias, float* Wp, float* Bp
 // ---------------------------------------------------------------------------------------
 // the fused layer kernel
 // ---------------------------------------------------------------------------------------
-template <int T, int OPL, int F, int NW>
+// UM = 0: u_hat computed here in FP32 from emb and the packed weights;
+// UM = 1 / 2: u_hat was materialised by the tcgen05 GEMM (uhat_gemm.cu) as bf16 / fp32 in the
+//             streaming layout [frame pair][i][q*(T/4)+k4][lane*4+k%4][2] and is only loaded
+//             here (F must be 2 = one frame pair per warp).
+template <int T, int OPL, int F, int NW, int UM>
 __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams p) {
+  static_assert(UM == 0 || F == 2, "u_hat streaming mode works on frame pairs");
   constexpr int OP = 32 * OPL;
   constexpr int T4 = T / 4;
   constexpr int NT = NW * 32;
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
   const int ni = max(0, i_hi - i_lo);
 
   float* xs = smem;                // [F][Ic][T]   window-gathered inputs of this CTA's i range
-  float* red = xs + F * p.Ic * T;  // [NW][E]      per-warp partial t, later the reduced total
+  float* red = xs + (UM == 0 ? F * p.Ic * T : 0);  // [NW][E] per-warp partial t, later the total
   float* tsum = red + NW * E;      // [2][E]       CTA partial for the cluster exchange
   float* vacc = tsum + 2 * E;      // [E]          Vacc = sum of squashed outputs so far
   float* vlast = vacc + E;         // [E]          last squashed output
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
 
   for (int s = 0; s < p.nsteps; ++s) {
     // ---- (1) window gather (naive:150-151) of this CTA's input capsules into smem --------
-    for (int idx = tid; idx < F * ni * T; idx += NT) {
+    for (int idx = tid; UM == 0 && idx < F * ni * T; idx += NT) {
       const int l = idx % T;
       const int ii = (idx / T) % ni;
       const int f = idx / (T * ni);
@@ -154,15 +159,67 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
             ta[f][q][k] = 0.f;
           }
 
+      // streaming mode: frame pair index of this group at this step, and a one-capsule-ahead
+      // register prefetch of the materialised u_hat
+      constexpr int RAWN = (UM == 1) ? OPL * T4 : (UM == 2 ? 2 * OPL * T4 : 1);
+      uint4 raw[RAWN];
+      const long long gg = p.sdr ? ((long long)s * p.halfB + group) : (long long)group;
+      const size_t ustride_i = (size_t)OPL * T4 * 128 * 2;  // elements per (pair, i)
+      auto load_raw = [&](int i, uint4(&dst)[RAWN]) {
+        if (UM == 1) {
+          const uint4* src = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const uint16_t*>(p.u) + ((size_t)gg * p.I + i) * ustride_i);
+#pragma unroll
+          for (int m = 0; m < OPL * T4; ++m) dst[m] = __ldg(src + m * 32 + lane);
+        } else if (UM == 2) {
+          const uint4* src = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const float*>(p.u) + ((size_t)gg * p.I + i) * ustride_i);
+#pragma unroll
+          for (int m = 0; m < OPL * T4; ++m) {
+            dst[2 * m] = __ldg(src + (m * 32 + lane) * 2);
+            dst[2 * m + 1] = __ldg(src + (m * 32 + lane) * 2 + 1);
+          }
+        }
+      };
+      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
+
       for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[F][OPL][T];
         float a[F][OPL];
         const float4* xrow = reinterpret_cast<const float4*>(xs) + (size_t)(i - i_lo) * T4;
+        if (UM != 0) {
+          // unpack the prefetched registers: element (k_in, f) of chunk m=(q,k4) sits at 2*k_in+f
+#pragma unroll
+          for (int q = 0; q < OPL; ++q)
+#pragma unroll
+            for (int k4 = 0; k4 < T4; ++k4) {
+              const int m = q * T4 + k4;
+              if (UM == 1) {
+                const uint32_t w[4] = {raw[m].x, raw[m].y, raw[m].z, raw[m].w};
+#pragma unroll
+                for (int kin = 0; kin < 4; ++kin) {
+                  u[0][q][k4 * 4 + kin] = __uint_as_float(w[kin] << 16);
+                  u[F - 1][q][k4 * 4 + kin] = __uint_as_float(w[kin] & 0xffff0000u);
+                }
+              } else {
+                const uint32_t w[8] = {raw[(2 * m) % RAWN].x, raw[(2 * m) % RAWN].y,
+                                       raw[(2 * m) % RAWN].z, raw[(2 * m) % RAWN].w,
+                                       raw[(2 * m + 1) % RAWN].x, raw[(2 * m + 1) % RAWN].y,
+                                       raw[(2 * m + 1) % RAWN].z, raw[(2 * m + 1) % RAWN].w};
+#pragma unroll
+                for (int kin = 0; kin < 4; ++kin) {
+                  u[0][q][k4 * 4 + kin] = __uint_as_float(w[2 * kin]);
+                  u[F - 1][q][k4 * 4 + kin] = __uint_as_float(w[2 * kin + 1]);
+                }
+              }
+            }
+          if (i + NW < i_hi) load_raw(i + NW, raw);
+        }
 #pragma unroll
         for (int q = 0; q < OPL; ++q) {
           const int jp = q * 32 + lane;
 #pragma unroll
-          for (int k = 0; k < T; ++k) {
+          for (int k = 0; UM == 0 && k < T; ++k) {
             float4 w4[T4];
 #pragma unroll
             for (int c = 0; c < T4; ++c)
@@ -273,7 +330,14 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
       const int f = warp;
       const int chain = group * F + f;
       if (chain < p.nchains) {
-        const long long frame = p.sdr ? ((long long)chain * p.S + s) : chain;
+        long long frame = p.sdr ? ((long long)chain * p.S + s) : chain;
+        bool frame_ok = true;
+        if (UM != 0 && !p.sdr) {  // DR on frame pairs: group -> (s, utterance pair)
+          const int ss = group / p.halfB, bb = 2 * (group % p.halfB) + f;
+          frame = (long long)bb * p.S + ss;
+          frame_ok = bb < p.B;
+        }
+        if (UM != 0 && p.sdr) frame_ok = chain < p.B;
         const float* vf = vlast + (size_t)f * OPL * T * 32;
         float mean = 0.f, rstd = 1.f;
         const bool do_ln = p.ln_gamma != nullptr;
@@ -305,8 +369,8 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
             for (int k = 0; k < D; ++k) {
               float y = vf[(q * T + k) * 32 + lane];
               if (do_ln) y = (y - mean) * rstd * __ldg(p.ln_gamma + j * D + k) + __ldg(p.ln_beta + j * D + k);
-              if (p.dropout_mask) y *= __ldg(p.dropout_mask + (frame * O + j) * D + k);
-              if (p.out_caps) p.out_caps[(frame * O + j) * D + k] = y;
+              if (p.dropout_mask && frame_ok) y *= __ldg(p.dropout_mask + (frame * O + j) * D + k);
+              if (p.out_caps && frame_ok) p.out_caps[(frame * O + j) * D + k] = y;
               l2 = fmaf(y, y, l2);
             }
           }
@@ -326,7 +390,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
           const float hr = 1.0f / sqrtf(warp_sum(sq) / (float)O + p.ln_eps);
           for (int q = 0; q < OPL; ++q) {
             const int j = q * 32 + lane;
-            if (j < O)
+            if (j < O && frame_ok)
               p.out_logits[frame * O + j] =
                   (len[q] - hm) * hr * __ldg(p.head_gamma + j) + __ldg(p.head_beta + j);
           }
@@ -343,10 +407,10 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
 // ---------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------
-template <int T, int OPL, int F, int NW>
+template <int T, int OPL, int F, int NW, int UM>
 static cudaError_t launch_variant(const RouteParams& p, int groups, size_t smem_bytes,
                                   cudaStream_t stream) {
-  auto kern = route_layer_kernel<T, OPL, F, NW>;
+  auto kern = route_layer_kernel<T, OPL, F, NW, UM>;
   cudaError_t err =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
@@ -365,17 +429,33 @@ static cudaError_t launch_variant(const RouteParams& p, int groups, size_t smem_
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-size_t route_layer_smem_bytes(int T, int OPL, int F, int NW, int Ic) {
+size_t route_layer_smem_bytes(int T, int OPL, int F, int NW, int Ic, int um) {
   const size_t E = (size_t)F * OPL * T * 32;
-  return sizeof(float) * ((size_t)F * Ic * T + (size_t)NW * E + 4 * E);
+  return sizeof(float) * ((um == 0 ? (size_t)F * Ic * T : 0) + (size_t)NW * E + 4 * E);
 }
 
 #define SRF_VARIANT(T_, OPL_, F_)                                                    \
   if (T == T_ && OPL == OPL_ && F == F_)                                             \
-    return launch_variant<T_, OPL_, F_, SRF_NW>(p, groups, smem_bytes, stream);
+    return launch_variant<T_, OPL_, F_, SRF_NW, 0>(p, groups, smem_bytes, stream);
+#define SRF_VARIANT_U(T_, OPL_)                                                      \
+  if (T == T_ && OPL == OPL_ && F == 2 && um == 1)                                   \
+    return launch_variant<T_, OPL_, 2, SRF_NW, 1>(p, groups, smem_bytes, stream);    \
+  if (T == T_ && OPL == OPL_ && F == 2 && um == 2)                                   \
+    return launch_variant<T_, OPL_, 2, SRF_NW, 2>(p, groups, smem_bytes, stream);
 
 cudaError_t launch_route_layer(const RouteParams& p, int T, int OPL, int F, int groups,
-                               size_t smem_bytes, cudaStream_t stream) {
+                               size_t smem_bytes, int um, cudaStream_t stream) {
+  if (um != 0) {
+    SRF_VARIANT_U(8, 1)
+    SRF_VARIANT_U(8, 2)
+    SRF_VARIANT_U(8, 4)
+    SRF_VARIANT_U(16, 1)
+    SRF_VARIANT_U(16, 2)
+    SRF_VARIANT_U(20, 1)
+    SRF_VARIANT_U(20, 2)
+    SRF_VARIANT_U(32, 1)
+    return cudaErrorInvalidValue;
+  }
   SRF_VARIANT(8, 1, 4)
   SRF_VARIANT(8, 1, 2)
   SRF_VARIANT(8, 1, 1)

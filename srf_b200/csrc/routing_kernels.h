@@ -27,6 +27,9 @@ struct RouteParams {
   int nchains;  // SDR: B, DR: B*S
   int nsteps;   // SDR: S, DR: 1
   float ln_eps, length_eps;
+  const void* u;  // materialised u_hat (streaming modes), else null
+  int halfB;      // frame pairs per time step = ceil(B/2)
+  int nstage;     // streaming kernel: depth of the shared-memory u_hat ring
 };
 
 // u_hat GEMM (uhat_gemm.cu)
@@ -46,10 +49,16 @@ struct UhatParams {
 void launch_pack_weights(const float* W, const float* bias, float* Wp, float* Bp, int I, int O,
                          int D, int d, int T, int OP, cudaStream_t stream);
 
-size_t route_layer_smem_bytes(int T, int OPL, int F, int NW, int Ic);
+size_t route_layer_smem_bytes(int T, int OPL, int F, int NW, int Ic, int um);
 int route_layer_max_F(int T, int OPL);
 cudaError_t launch_route_layer(const RouteParams& p, int T, int OPL, int F, int groups,
-                               size_t smem_bytes, cudaStream_t stream);
+                               size_t smem_bytes, int um, cudaStream_t stream);
+
+// streaming routing kernel over a materialised u_hat (routing_stream.cu)
+size_t route_stream_fixed_smem(int T, int OPL, int C, int max_stages);
+size_t route_stream_stage_bytes(int T, int OPL, bool bf16);
+cudaError_t launch_route_stream(const RouteParams& p, int T, int OPL, bool bf16, int groups,
+                                size_t smem_bytes, cudaStream_t stream);
 
 void launch_pack_weights_mma(const float* W, const float* bias, float* Wm, float* Bm, int I, int O,
                              int D, int d, int T, int OPL, int KC, cudaStream_t stream);

@@ -1,0 +1,490 @@
+// routing_stream.cu -- routing iterations over a MATERIALISED u_hat (tensor-core path), sm_100a.
+//
+// u_hat of the whole layer was produced by the tcgen05 GEMM (uhat_gemm.cu) in the layout
+//   [frame pair g][input capsule i][chunk m = q*(T/4)+k4][lane*4 + k%4][pair member f]   (bf16|fp32)
+// so that for one (g, i) every lane (= output capsule j) owns 16-byte chunks and a warp's read is
+// one contiguous slab.  This kernel is the sequential part of the layer
+// (tfsr/model/sequence_router_naive.py:162-191): SDR frame recurrence or DR iterations, squash,
+// LayerNorm + dropout, head.  It is a streaming kernel:
+//
+//   warp NW     : producer.  One lane issues cp.async.bulk (TMA 1-D) copies of the CTA's slice of
+//                 u_hat into a shared-memory ring, NW capsules per stage, running ahead of the
+//                 consumers across frames (u_hat does not depend on the recurrence).
+//   warps 0..NW-1: consumers.  lane = output capsule; u_hat chunk -> registers, agreement with
+//                 Vacc, softmax over output capsules by warp shuffles, t += c*u_hat in registers.
+//   warps NW+1,+2: output.  LayerNorm(O*D), dropout mask, head and the global stores of frame s run
+//                 off a double-buffered copy of v while the consumers already work on frame s+1.
+//
+// The partial sums of the C CTAs of a cluster (input capsules are split between them) are
+// exchanged by pushing into the peers' shared memory (st.shared::cluster) and signalling the
+// peers' mbarriers -- no cluster-wide barrier on the per-frame critical path.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "routing_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace srf {
+
+namespace {
+
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void fence_cluster() {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(ptx::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+
+enum { BAR_COMPUTE = 1, BAR_READY0 = 2, BAR_READY1 = 3, BAR_FREE0 = 4, BAR_FREE1 = 5 };
+
+}  // namespace
+
+template <int T, int OPL, int NW, bool BF16>
+__global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const RouteParams p) {
+  constexpr int T4 = T / 4;
+  constexpr int NCT = NW * 32;                 // consumer threads
+  constexpr int NSYNC = (NW + 2) * 32;         // consumers + the two output warps
+  constexpr int E = 2 * OPL * T * 32;          // one t tile: ((f*OPL+q)*T+k)*32+lane
+  constexpr int SLAB = OPL * T4 * 128 * 2 * (BF16 ? 2 : 4);  // bytes of u_hat per (pair, capsule)
+  constexpr int STAGE = NW * SLAB;
+  constexpr int RAWN = SLAB / 512;             // uint4 per lane per capsule
+  constexpr float LOG2E = 1.4426950408889634f;
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, NSTAGE = p.nstage;
+  const int rank = C > 1 ? (int)cluster_rank() : 0;
+  const int group = blockIdx.x / C;
+  const int i_lo = rank * p.Ic;
+  const int i_hi = min(p.I, i_lo + p.Ic);
+  const int O = p.O, D = p.D;
+
+  uint8_t* ring = smem_raw;                                        // [NSTAGE][STAGE]
+  float* red = reinterpret_cast<float*>(ring + (size_t)NSTAGE * STAGE);  // [NW][E], then total [E]
+  float* xbuf = red + NW * E;                                      // [2][C][E] peers' partial sums
+  float* vacc = xbuf + 2 * C * E;                                  // [E]
+  float* vout = vacc + E;                                          // [2][E]
+  uint64_t* full = reinterpret_cast<uint64_t*>(vout + 2 * E);      // [NSTAGE]
+  uint64_t* empty = full + NSTAGE;                                 // [NSTAGE]
+  uint64_t* xfull = empty + NSTAGE;                                // [2]
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], NW);
+    }
+    ptx::mbar_init(&xfull[0], C * NW);
+    ptx::mbar_init(&xfull[1], C * NW);
+    ptx::fence_barrier_init();
+  }
+  for (int e = tid; e < E; e += blockDim.x) vacc[e] = 0.f;
+  __syncthreads();
+  if (C > 1) cluster_sync_all();  // peers' barriers are initialised before anybody pushes
+
+  const size_t pair_stride = (size_t)p.I * SLAB;  // bytes per frame pair
+
+  if (warp == NW) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int s = 0; s < p.nsteps; ++s) {
+        const long long gg = p.sdr ? ((long long)s * p.halfB + group) : (long long)group;
+        const uint8_t* src_pair = reinterpret_cast<const uint8_t*>(p.u) + (size_t)gg * pair_stride;
+        for (int pass = 0; pass < p.iters; ++pass) {
+          for (int base = i_lo; base < i_hi; base += NW, ++n) {
+            const int st = n % NSTAGE;
+            const int cnt = min(NW, i_hi - base);
+            ptx::mbar_wait(&empty[st], ((n / NSTAGE) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)cnt * SLAB);
+            ptx::bulk_g2s(ring + (size_t)st * STAGE, src_pair + (size_t)base * SLAB,
+                          (uint32_t)cnt * SLAB, &full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp < NW) {
+    // ============================== consumers ==============================
+    uint32_t n = 0;       // stage counter (mirrors the producer)
+    uint32_t npass = 0;   // exchange counter
+    for (int s = 0; s < p.nsteps; ++s) {
+      for (int pass = 0; pass < p.iters; ++pass) {
+        const bool last_pass = pass == p.iters - 1;
+        float va[2][OPL][T], ta[2][OPL][T];
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int q = 0; q < OPL; ++q)
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+              va[f][q][k] = vacc[((f * OPL + q) * T + k) * 32 + lane];
+              ta[f][q][k] = 0.f;
+            }
+
+        for (int base = i_lo; base < i_hi; base += NW, ++n) {
+          const int st = n % NSTAGE;
+          const int i = base + warp;
+          uint4 raw[RAWN];
+          ptx::mbar_wait(&full[st], (n / NSTAGE) & 1);
+          if (i < i_hi) {
+            const uint4* slab =
+                reinterpret_cast<const uint4*>(ring + (size_t)st * STAGE + (size_t)warp * SLAB);
+#pragma unroll
+            for (int m = 0; m < RAWN; ++m)
+              raw[m] = BF16 ? slab[m * 32 + lane] : slab[(m >> 1) * 64 + lane * 2 + (m & 1)];
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&empty[st]);
+          if (i >= i_hi) continue;
+
+          float u[2][OPL][T];
+#pragma unroll
+          for (int q = 0; q < OPL; ++q)
+#pragma unroll
+            for (int k4 = 0; k4 < T4; ++k4) {
+              const int m = q * T4 + k4;
+              if (BF16) {
+                const uint32_t w[4] = {raw[m].x, raw[m].y, raw[m].z, raw[m].w};
+#pragma unroll
+                for (int kin = 0; kin < 4; ++kin) {
+                  u[0][q][k4 * 4 + kin] = __uint_as_float(w[kin] << 16);
+                  u[1][q][k4 * 4 + kin] = __uint_as_float(w[kin] & 0xffff0000u);
+                }
+              } else {
+                const uint4 r0 = raw[(2 * m) % RAWN], r1 = raw[(2 * m + 1) % RAWN];
+                const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int kin = 0; kin < 4; ++kin) {
+                  u[0][q][k4 * 4 + kin] = __uint_as_float(w[2 * kin]);
+                  u[1][q][k4 * 4 + kin] = __uint_as_float(w[2 * kin + 1]);
+                }
+              }
+            }
+          // agreement with the accumulated outputs (naive:205 / :223 / :240)
+          float a[2][OPL];
+#pragma unroll
+          for (int q = 0; q < OPL; ++q) {
+            const int jp = q * 32 + lane;
+            const bool valid = (jp < O) && !(p.mask0 && jp == 0);
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              float acc = 0.f;
+#pragma unroll
+              for (int k = 0; k < T; ++k) acc = fmaf(u[f][q][k], va[f][q][k], acc);
+              a[f][q] = valid ? acc : -CUDART_INF_F;
+            }
+          }
+          // coupling softmax over output capsules (naive:202 / :225 / :241) + weighted sum
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            float m = a[f][0];
+#pragma unroll
+            for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[f][q]);
+            m = wmax(m);
+            float ex[OPL];
+            float z = 0.f;
+#pragma unroll
+            for (int q = 0; q < OPL; ++q) {
+              ex[q] = exp2f((a[f][q] - m) * LOG2E);
+              z += ex[q];
+            }
+            z = wsum(z);
+            const float inv = 1.0f / z;
+#pragma unroll
+            for (int q = 0; q < OPL; ++q) {
+              const float c = ex[q] * inv;
+#pragma unroll
+              for (int k = 0; k < T; ++k) ta[f][q][k] = fmaf(c, u[f][q][k], ta[f][q][k]);
+            }
+          }
+        }
+
+        // ---- reduce t over the consumer warps ---------------------------------------------
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int q = 0; q < OPL; ++q)
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+              red[warp * E + ((f * OPL + q) * T + k) * 32 + lane] = ta[f][q][k];
+        named_sync(BAR_COMPUTE, NCT);
+        const int par = npass & 1;
+        if (C > 1) {
+          // push this CTA's partial into every peer's xbuf[par][rank], then signal the peers
+          const uint32_t xb = ptx::smem_u32(xbuf + ((size_t)par * C + rank) * E);
+          for (int e = tid; e < E; e += NCT) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) acc += red[w * E + e];
+            for (int r = 0; r < C; ++r) st_cluster_f32(map_to_rank(xb + e * 4, r), acc);
+          }
+          fence_cluster();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t bar = ptx::smem_u32(&xfull[par]);
+            for (int r = 0; r < C; ++r) mbar_arrive_remote(map_to_rank(bar, r));
+          }
+          while (!mbar_try_wait_cluster(&xfull[par], (npass >> 1) & 1)) {
+          }
+          named_sync(BAR_COMPUTE, NCT);  // everybody is done reading red[] partials
+          for (int e = tid; e < E; e += NCT) {
+            float acc = 0.f;
+            for (int r = 0; r < C; ++r) acc += xbuf[((size_t)par * C + r) * E + e];
+            red[e] = acc;
+          }
+        } else {
+          float acc[(E + NCT - 1) / NCT];
+#pragma unroll
+          for (int m = 0; m < (E + NCT - 1) / NCT; ++m) {
+            const int e = tid + m * NCT;
+            acc[m] = 0.f;
+            if (e < E) {
+#pragma unroll
+              for (int w = 0; w < NW; ++w) acc[m] += red[w * E + e];
+            }
+          }
+          named_sync(BAR_COMPUTE, NCT);
+#pragma unroll
+          for (int m = 0; m < (E + NCT - 1) / NCT; ++m) {
+            const int e = tid + m * NCT;
+            if (e < E) red[e] = acc[m];
+          }
+        }
+        ++npass;
+        named_sync(BAR_COMPUTE, NCT);
+
+        // ---- squash (naive:248-253), Vacc update, hand v to the output warps ------------------
+        if (last_pass && s >= 2) named_sync(BAR_FREE0 + (s & 1), NSYNC);
+        if (tid < 2 * OPL * 32) {
+          const int fq = tid >> 5;
+          float t[T];
+          float n2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < T; ++k) {
+            t[k] = red[(fq * T + k) * 32 + lane];
+            n2 = fmaf(t[k], t[k], n2);
+          }
+          const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
+          float* vo = vout + (size_t)(s & 1) * E;
+#pragma unroll
+          for (int k = 0; k < T; ++k) {
+            const int e = (fq * T + k) * 32 + lane;
+            const float v = t[k] * scale;
+            if (last_pass) {
+              vo[e] = v;
+              vacc[e] = p.sdr ? v : 0.f;  // SDR: next frame starts from this output (naive:167)
+            } else {
+              vacc[e] += v;
+            }
+          }
+        }
+        named_sync(BAR_COMPUTE, NCT);
+        if (last_pass) named_arrive(BAR_READY0 + (s & 1), NSYNC);
+      }
+    }
+  } else if (warp <= NW + 2) {
+    // ============================== output warps (one per pair member) ==============================
+    const int f = warp - (NW + 1);
+    const bool do_ln = p.ln_gamma != nullptr;
+    const bool do_head = p.head_gamma != nullptr;
+    float gam[OPL][T], bet[OPL][T], hg[OPL], hb[OPL];
+#pragma unroll
+    for (int q = 0; q < OPL; ++q) {
+      const int j = q * 32 + lane;
+      hg[q] = (do_head && j < O) ? __ldg(p.head_gamma + j) : 1.f;
+      hb[q] = (do_head && j < O) ? __ldg(p.head_beta + j) : 0.f;
+#pragma unroll
+      for (int k = 0; k < T; ++k) {
+        const bool ok = do_ln && j < O && k < D;
+        gam[q][k] = ok ? __ldg(p.ln_gamma + j * D + k) : 1.f;
+        bet[q][k] = ok ? __ldg(p.ln_beta + j * D + k) : 0.f;
+      }
+    }
+    const float inv_n = 1.0f / (float)(O * D);
+    for (int s = 0; s < p.nsteps; ++s) {
+      named_sync(BAR_READY0 + (s & 1), NSYNC);
+      const float* vf = vout + (size_t)(s & 1) * E + (size_t)f * OPL * T * 32;
+      float y[OPL][T];
+#pragma unroll
+      for (int q = 0; q < OPL; ++q)
+#pragma unroll
+        for (int k = 0; k < T; ++k) y[q][k] = vf[(q * T + k) * 32 + lane];
+      if (s + 2 < p.nsteps) named_arrive(BAR_FREE0 + (s & 1), NSYNC);
+
+      long long frame;
+      bool ok;
+      if (p.sdr) {
+        const int b = group * 2 + f;
+        ok = b < p.B;
+        frame = (long long)b * p.S + s;
+      } else {
+        const int ss = group / p.halfB, bb = 2 * (group % p.halfB) + f;
+        ok = bb < p.B;
+        frame = (long long)bb * p.S + ss;
+      }
+      if (!ok) continue;
+      if (do_ln) {
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < OPL; ++q)
+#pragma unroll
+          for (int k = 0; k < T; ++k)
+            if (q * 32 + lane < O && k < D) sum += y[q][k];
+        const float mean = wsum(sum) * inv_n;
+        float sq = 0.f;
+#pragma unroll
+        for (int q = 0; q < OPL; ++q)
+#pragma unroll
+          for (int k = 0; k < T; ++k)
+            if (q * 32 + lane < O && k < D) {
+              const float dv = y[q][k] - mean;
+              sq = fmaf(dv, dv, sq);
+            }
+        const float rstd = 1.0f / sqrtf(wsum(sq) * inv_n + p.ln_eps);
+#pragma unroll
+        for (int q = 0; q < OPL; ++q)
+#pragma unroll
+          for (int k = 0; k < T; ++k) y[q][k] = (y[q][k] - mean) * rstd * gam[q][k] + bet[q][k];
+      }
+      float len[OPL];
+#pragma unroll
+      for (int q = 0; q < OPL; ++q) {
+        const int j = q * 32 + lane;
+        float l2 = 0.f;
+        if (j < O) {
+#pragma unroll
+          for (int k = 0; k < T; ++k)
+            if (k < D) {
+              float v = y[q][k];
+              if (p.dropout_mask) v *= __ldg(p.dropout_mask + (frame * O + j) * D + k);
+              if (p.out_caps) p.out_caps[(frame * O + j) * D + k] = v;
+              l2 = fmaf(v, v, l2);
+            }
+        }
+        len[q] = sqrtf(l2 + p.length_eps);  // naive:256-258
+      }
+      if (do_head) {  // ln_output over the capsule lengths (naive:193)
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < OPL; ++q)
+          if (q * 32 + lane < O) sum += len[q];
+        const float hm = wsum(sum) / (float)O;
+        float sq = 0.f;
+#pragma unroll
+        for (int q = 0; q < OPL; ++q)
+          if (q * 32 + lane < O) {
+            const float dv = len[q] - hm;
+            sq = fmaf(dv, dv, sq);
+          }
+        const float hr = 1.0f / sqrtf(wsum(sq) / (float)O + p.ln_eps);
+#pragma unroll
+        for (int q = 0; q < OPL; ++q) {
+          const int j = q * 32 + lane;
+          if (j < O) p.out_logits[frame * O + j] = (len[q] - hm) * hr * hg[q] + hb[q];
+        }
+      }
+    }
+  }
+
+  // nobody leaves while a peer may still push into this CTA's shared memory
+  __syncthreads();
+  if (C > 1) cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------
+template <int T, int OPL, bool BF16>
+static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_t smem_bytes,
+                                         cudaStream_t stream) {
+  auto kern = route_stream_kernel<T, OPL, SRF_NW, BF16>;
+  cudaError_t err =
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * p.C));
+  cfg.blockDim = dim3((SRF_NW + 3) * 32);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+// fixed (non-ring) shared memory of the streaming kernel
+size_t route_stream_fixed_smem(int T, int OPL, int C, int max_stages) {
+  const size_t E = (size_t)2 * OPL * T * 32;
+  return sizeof(float) * ((size_t)SRF_NW * E + (size_t)2 * C * E + 3 * E) +
+         sizeof(uint64_t) * (2 * (size_t)max_stages + 2) + 128;
+}
+size_t route_stream_stage_bytes(int T, int OPL, bool bf16) {
+  return (size_t)SRF_NW * OPL * (T / 4) * 128 * 2 * (bf16 ? 2 : 4);
+}
+
+#define SRF_STREAM(T_, OPL_)                                                            \
+  if (T == T_ && OPL == OPL_)                                                           \
+    return bf16 ? launch_stream_variant<T_, OPL_, true>(p, groups, smem_bytes, stream)  \
+                : launch_stream_variant<T_, OPL_, false>(p, groups, smem_bytes, stream);
+
+cudaError_t launch_route_stream(const RouteParams& p, int T, int OPL, bool bf16, int groups,
+                                size_t smem_bytes, cudaStream_t stream) {
+  SRF_STREAM(8, 1)
+  SRF_STREAM(8, 2)
+  SRF_STREAM(8, 4)
+  SRF_STREAM(16, 1)
+  SRF_STREAM(16, 2)
+  SRF_STREAM(20, 1)
+  SRF_STREAM(20, 2)
+  SRF_STREAM(32, 1)
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace srf

@@ -230,3 +230,75 @@ def test_cuda_path_matches_reference_goldens(name):
   assert rel_err(logits, g["logits"]) < REL_TOL_FP32
   lens = [int(n) // 4 for n in g["input_lengths"]]
   assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(g["logits"], lens)
+
+
+# ----------------------------------------------------------------------------------------
+# tensor-core u_hat path (tcgen05 GEMM + streaming routing kernel)
+# north_star tolerance: 1e-2 relative in BF16 u_hat mode; TF32 operands with fp32 u_hat storage
+# are held to 5e-3 here.
+# ----------------------------------------------------------------------------------------
+TENSOR_TOL = {"tf32": 5e-3, "bf16": 1e-2}
+TENSOR_LAYER_CASES = [
+    (2, 9, 6, 8, 5, 8, 1, 1),
+    (3, 5, 60, 8, 30, 8, 1, 1),
+    (2, 6, 30, 8, 63, 8, 1, 1),
+    (8, 5, 30, 8, 30, 8, 3, 3),
+    (64, 3, 60, 20, 30, 20, 2, 2),
+    (5, 4, 30, 20, 32, 20, 2, 2),      # odd batch: the last frame pair is half empty
+    (2, 5, 7, 16, 9, 16, 0, 0),
+    (1, 6, 5, 32, 6, 32, 4, 4),
+    (2, 4, 9, 8, 100, 8, 0, 1),
+    (3, 4, 9, 4, 10, 12, 1, 0),        # d != D
+]
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_uhat_gemm_matches_oracle(mode):
+  from srf_b200 import routing
+  for case in TENSOR_LAYER_CASES:
+    B, S, H, d, O, D, lpad, rpad = case
+    emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=5)
+    ref = o.prediction_vectors(o.window_gather(emb.double(), lpad, rpad), W.double(), bias.double())
+    out = routing.uhat_fwd(emb.cuda(), W.cuda(), bias.cuda(), lpad, rpad, mode)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < TENSOR_TOL[mode], case
+
+
+@pytest.mark.parametrize("case", TENSOR_LAYER_CASES)
+@pytest.mark.parametrize("sdr", [True, False])
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_tensor_path_single_layer(case, sdr, mode):
+  B, S, H, d, O, D, lpad, rpad = case
+  emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=17)
+  for iters, last in ((1, False), (3, True)):
+    ref = o.route_layer(emb.double(), W.double(), bias.double(), lpad, rpad, iters, sdr, last)
+    caps, _ = _run_layer(emb, W, bias, lpad, rpad, iters, sdr, last, uhat_mode=mode)
+    assert rel_err(caps, ref) < TENSOR_TOL[mode], (iters, last)
+    if last:
+      assert torch.count_nonzero(caps[:, :, 0]) == 0
+
+
+def test_tensor_path_needs_d_multiple_of_4():
+  emb, W, bias = _mk_layer(2, 4, 6, 6, 5, 8, 1, seed=1)
+  with pytest.raises(ValueError):
+    _run_layer(emb, W, bias, 0, 0, 1, True, False, uhat_mode="tf32")
+
+
+@pytest.mark.parametrize("case", STACK_CASES, ids=[c[0] for c in STACK_CASES])
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_tensor_path_full_stack(case, mode):
+  from srf_b200 import RoutingStack
+  _, L, PH, CH, class_n, DIM, lpad, rpad, iters, sdr, B, S = case
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1)
+  p32 = o.init_params(shapes, class_n, seed=11, random_ln=True)
+  emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(12))
+  ref_logits = o.route_stack(emb.double(), p32.to(torch.float64), lpad, rpad, iters, sdr)
+  stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, sdr, seed=0, uhat_mode=mode)
+  stack.load_oracle_params(p32)
+  logits = stack.forward(emb.cuda())
+  torch.cuda.synchronize()
+  assert "uhat_gemm_kernel" in stack.handle.last_kernel
+  assert rel_err(logits, ref_logits) < TENSOR_TOL[mode]
+  lens = [S] + [max(1, S - 3)] * (B - 1)
+  assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(ref_logits, lens)

@@ -38,7 +38,7 @@ struct srf_handle {
   std::vector<PackedWeights> packed;
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
-  int force_F = 0, force_C = 0, no_stream = 0;
+  int force_F = 0, force_C = 0, no_stream = 0, max_stages = 0;
   // tensor-core path
   std::vector<PackedWeights> packed_mma;
   void* ubuf = nullptr;  // materialised u_hat of one layer
@@ -105,6 +105,7 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_FORCE_F")) h->force_F = atoi(s);
   if (const char* s = getenv("SRF_FORCE_C")) h->force_C = atoi(s);
   if (const char* s = getenv("SRF_NO_STREAM")) h->no_stream = atoi(s);
+  if (const char* s = getenv("SRF_STREAM_STAGES")) h->max_stages = atoi(s);
   *out = h;
   return 0;
 }
@@ -493,7 +494,8 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
   p.halfB = halfB;
 
   p.nstage = 0;
-  if (um != 0 && !h->no_stream) {
+  // (fp32 u_hat storage stays on the in-kernel register-prefetch variant)
+  if (um == 1 && !h->no_stream) {
     // streaming kernel: TMA-fed ring + warp-specialised output; needs >= 2 ring stages
     int Cs = C;
     if (Cs * groups > h->num_sms) Cs = pow2_floor(h->num_sms / groups > 0 ? h->num_sms / groups : 1);
@@ -502,6 +504,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
     if (fixed + 2 * stage <= (size_t)h->max_smem) {
       int nstage = (int)(((size_t)h->max_smem - fixed) / stage);
       if (nstage > 16) nstage = 16;
+      if (h->max_stages >= 2 && nstage > h->max_stages) nstage = h->max_stages;
       p.C = Cs;
       p.Ic = (I + Cs - 1) / Cs;
       p.nstage = nstage;

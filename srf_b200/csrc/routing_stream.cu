@@ -81,18 +81,34 @@ __device__ __forceinline__ void cluster_sync_all() {
                    : "memory");
 }
 
-enum { BAR_COMPUTE = 1, BAR_READY0 = 2, BAR_READY1 = 3, BAR_FREE0 = 4, BAR_FREE1 = 5 };
+enum { BAR_COMPUTE = 1 };
+
+// remote store of 4 floats into a peer CTA's shared memory that completes (by byte count) on
+// that peer's mbarrier: data visibility and signalling in one instruction, no fences.
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+          remote_addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
+      : "memory");
+}
 
 }  // namespace
 
-template <int T, int OPL, int NW, bool BF16>
-__global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const RouteParams p) {
+// NSLOT = input capsules per ring stage; FPW = pair members (frames) per consumer warp.
+// FPW = 1: 2*NSLOT consumer warps, warp w works on capsule slot w>>1 for pair member w&1;
+// FPW = 2: NSLOT consumer warps, each handles both members (for variants with a large per-lane
+// state O*D/32 that would not fit the register budget of 2*NSLOT+3 warps).
+template <int T, int OPL, int NSLOT, int FPW, bool BF16>
+__global__ void __launch_bounds__((NSLOT * (2 / FPW) + 3) * 32, 1)
+route_stream_kernel(const RouteParams p) {
   constexpr int T4 = T / 4;
-  constexpr int NCT = NW * 32;                 // consumer threads
-  constexpr int NSYNC = (NW + 2) * 32;         // consumers + the two output warps
-  constexpr int E = 2 * OPL * T * 32;          // one t tile: ((f*OPL+q)*T+k)*32+lane
+  constexpr int NCW = NSLOT * (2 / FPW);       // consumer warps
+  constexpr int NCT = NCW * 32;                // consumer threads
+  constexpr int EF = OPL * T * 32;             // t tile of ONE pair member: (q*T+k)*32+lane
+  constexpr int E = 2 * EF;                    // both members: f*EF + ...
   constexpr int SLAB = OPL * T4 * 128 * 2 * (BF16 ? 2 : 4);  // bytes of u_hat per (pair, capsule)
-  constexpr int STAGE = NW * SLAB;
+  constexpr int STAGE = NSLOT * SLAB;
   constexpr int RAWN = SLAB / 512;             // uint4 per lane per capsule
   constexpr float LOG2E = 1.4426950408889634f;
 
@@ -106,21 +122,27 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
   const int O = p.O, D = p.D;
 
   uint8_t* ring = smem_raw;                                        // [NSTAGE][STAGE]
-  float* red = reinterpret_cast<float*>(ring + (size_t)NSTAGE * STAGE);  // [NW][E], then total [E]
-  float* xbuf = red + NW * E;                                      // [2][C][E] peers' partial sums
+  float* red = reinterpret_cast<float*>(ring + (size_t)NSTAGE * STAGE);  // [NSLOT][E] warp partials
+  float* xbuf = red + NSLOT * E;                                   // [2][C][E] CTA partial sums
   float* vacc = xbuf + 2 * C * E;                                  // [E]
   float* vout = vacc + E;                                          // [2][E]
   uint64_t* full = reinterpret_cast<uint64_t*>(vout + 2 * E);      // [NSTAGE]
   uint64_t* empty = full + NSTAGE;                                 // [NSTAGE]
   uint64_t* xfull = empty + NSTAGE;                                // [2]
+  uint64_t* vready = xfull + 2;                                    // [2] v of frame s is in vout[s&1]
+  uint64_t* vfree = vready + 2;                                    // [2] output warps are done with it
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], NW);
+      ptx::mbar_init(&empty[s], NCW);
     }
-    ptx::mbar_init(&xfull[0], C * NW);
-    ptx::mbar_init(&xfull[1], C * NW);
+    ptx::mbar_init(&xfull[0], 1);
+    ptx::mbar_init(&xfull[1], 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&vready[b], 1);
+      ptx::mbar_init(&vfree[b], 2);  // one arrive per output warp
+    }
     ptx::fence_barrier_init();
   }
   for (int e = tid; e < E; e += blockDim.x) vacc[e] = 0.f;
@@ -129,60 +151,70 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
 
   const size_t pair_stride = (size_t)p.I * SLAB;  // bytes per frame pair
 
-  if (warp == NW) {
+  if (warp == NCW) {
     // ============================== producer ==============================
     if (lane == 0) {
-      uint32_t n = 0;
+      int st = 0;
+      uint32_t ph = 0;
       for (int s = 0; s < p.nsteps; ++s) {
         const long long gg = p.sdr ? ((long long)s * p.halfB + group) : (long long)group;
         const uint8_t* src_pair = reinterpret_cast<const uint8_t*>(p.u) + (size_t)gg * pair_stride;
         for (int pass = 0; pass < p.iters; ++pass) {
-          for (int base = i_lo; base < i_hi; base += NW, ++n) {
-            const int st = n % NSTAGE;
-            const int cnt = min(NW, i_hi - base);
-            ptx::mbar_wait(&empty[st], ((n / NSTAGE) & 1) ^ 1);
+          for (int base = i_lo; base < i_hi; base += NSLOT) {
+            const int cnt = min(NSLOT, i_hi - base);
+            ptx::mbar_wait(&empty[st], ph ^ 1);
             ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)cnt * SLAB);
             ptx::bulk_g2s(ring + (size_t)st * STAGE, src_pair + (size_t)base * SLAB,
                           (uint32_t)cnt * SLAB, &full[st]);
+            if (++st == NSTAGE) {
+              st = 0;
+              ph ^= 1;
+            }
           }
         }
       }
     }
-  } else if (warp < NW) {
+  } else if (warp < NCW) {
     // ============================== consumers ==============================
-    uint32_t n = 0;       // stage counter (mirrors the producer)
+    const int slot = FPW == 1 ? (warp >> 1) : warp;   // capsule slot inside a stage
+    const int f0 = FPW == 1 ? (warp & 1) : 0;         // first pair member of this warp
+    int st = 0;
+    uint32_t ph = 0;
     uint32_t npass = 0;   // exchange counter
     for (int s = 0; s < p.nsteps; ++s) {
       for (int pass = 0; pass < p.iters; ++pass) {
         const bool last_pass = pass == p.iters - 1;
-        float va[2][OPL][T], ta[2][OPL][T];
+        float va[FPW][OPL][T], ta[FPW][OPL][T];
 #pragma unroll
-        for (int f = 0; f < 2; ++f)
+        for (int f = 0; f < FPW; ++f)
 #pragma unroll
           for (int q = 0; q < OPL; ++q)
 #pragma unroll
             for (int k = 0; k < T; ++k) {
-              va[f][q][k] = vacc[((f * OPL + q) * T + k) * 32 + lane];
+              va[f][q][k] = vacc[(f0 + f) * EF + (q * T + k) * 32 + lane];
               ta[f][q][k] = 0.f;
             }
 
-        for (int base = i_lo; base < i_hi; base += NW, ++n) {
-          const int st = n % NSTAGE;
-          const int i = base + warp;
+        for (int base = i_lo; base < i_hi; base += NSLOT) {
+          const int i = base + slot;
           uint4 raw[RAWN];
-          ptx::mbar_wait(&full[st], (n / NSTAGE) & 1);
+          ptx::mbar_wait(&full[st], ph);
           if (i < i_hi) {
             const uint4* slab =
-                reinterpret_cast<const uint4*>(ring + (size_t)st * STAGE + (size_t)warp * SLAB);
+                reinterpret_cast<const uint4*>(ring + (size_t)st * STAGE + (size_t)slot * SLAB);
 #pragma unroll
             for (int m = 0; m < RAWN; ++m)
               raw[m] = BF16 ? slab[m * 32 + lane] : slab[(m >> 1) * 64 + lane * 2 + (m & 1)];
           }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&empty[st]);
+          if (++st == NSTAGE) {
+            st = 0;
+            ph ^= 1;
+          }
           if (i >= i_hi) continue;
 
-          float u[2][OPL][T];
+          float u[FPW][OPL][T];
 #pragma unroll
           for (int q = 0; q < OPL; ++q)
 #pragma unroll
@@ -192,40 +224,64 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
                 const uint32_t w[4] = {raw[m].x, raw[m].y, raw[m].z, raw[m].w};
 #pragma unroll
                 for (int kin = 0; kin < 4; ++kin) {
-                  u[0][q][k4 * 4 + kin] = __uint_as_float(w[kin] << 16);
-                  u[1][q][k4 * 4 + kin] = __uint_as_float(w[kin] & 0xffff0000u);
+                  const float lo = __uint_as_float(w[kin] << 16);
+                  const float hi = __uint_as_float(w[kin] & 0xffff0000u);
+                  if (FPW == 2) {
+                    u[0][q][k4 * 4 + kin] = lo;
+                    u[FPW - 1][q][k4 * 4 + kin] = hi;
+                  } else {
+                    u[0][q][k4 * 4 + kin] = f0 ? hi : lo;
+                  }
                 }
               } else {
                 const uint4 r0 = raw[(2 * m) % RAWN], r1 = raw[(2 * m + 1) % RAWN];
                 const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int kin = 0; kin < 4; ++kin) {
-                  u[0][q][k4 * 4 + kin] = __uint_as_float(w[2 * kin]);
-                  u[1][q][k4 * 4 + kin] = __uint_as_float(w[2 * kin + 1]);
+                  const float lo = __uint_as_float(w[2 * kin]);
+                  const float hi = __uint_as_float(w[2 * kin + 1]);
+                  if (FPW == 2) {
+                    u[0][q][k4 * 4 + kin] = lo;
+                    u[FPW - 1][q][k4 * 4 + kin] = hi;
+                  } else {
+                    u[0][q][k4 * 4 + kin] = f0 ? hi : lo;
+                  }
                 }
               }
             }
           // agreement with the accumulated outputs (naive:205 / :223 / :240)
-          float a[2][OPL];
+          float a[FPW][OPL];
+          bool small = true;
 #pragma unroll
           for (int q = 0; q < OPL; ++q) {
             const int jp = q * 32 + lane;
             const bool valid = (jp < O) && !(p.mask0 && jp == 0);
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-              float acc = 0.f;
+            for (int f = 0; f < FPW; ++f) {
+              float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-              for (int k = 0; k < T; ++k) acc = fmaf(u[f][q][k], va[f][q][k], acc);
+              for (int k = 0; k < T; k += 2) {
+                acc0 = fmaf(u[f][q][k], va[f][q][k], acc0);
+                acc1 = fmaf(u[f][q][k + 1], va[f][q][k + 1], acc1);
+              }
+              const float acc = acc0 + acc1;
+              small = small && (fabsf(acc) < 60.f);
               a[f][q] = valid ? acc : -CUDART_INF_F;
             }
           }
-          // coupling softmax over output capsules (naive:202 / :225 / :241) + weighted sum
+          // coupling softmax over output capsules (naive:202 / :225 / :241) + weighted sum.
+          // softmax is shift invariant: when every logit of the warp is small the max
+          // subtraction (a 5-step shuffle chain) is skipped; otherwise the usual stable form.
+          const bool fast = __all_sync(0xffffffffu, small);
 #pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            float m = a[f][0];
+          for (int f = 0; f < FPW; ++f) {
+            float m = 0.f;
+            if (!fast) {
+              m = a[f][0];
 #pragma unroll
-            for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[f][q]);
-            m = wmax(m);
+              for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[f][q]);
+              m = wmax(m);
+            }
             float ex[OPL];
             float z = 0.f;
 #pragma unroll
@@ -244,70 +300,62 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
           }
         }
 
-        // ---- reduce t over the consumer warps ---------------------------------------------
+        // ---- reduce t over the capsule slots of this CTA -------------------------------------
 #pragma unroll
-        for (int f = 0; f < 2; ++f)
+        for (int f = 0; f < FPW; ++f)
 #pragma unroll
           for (int q = 0; q < OPL; ++q)
 #pragma unroll
             for (int k = 0; k < T; ++k)
-              red[warp * E + ((f * OPL + q) * T + k) * 32 + lane] = ta[f][q][k];
-        named_sync(BAR_COMPUTE, NCT);
+              red[slot * E + (f0 + f) * EF + (q * T + k) * 32 + lane] = ta[f][q][k];
         const int par = npass & 1;
-        if (C > 1) {
-          // push this CTA's partial into every peer's xbuf[par][rank], then signal the peers
-          const uint32_t xb = ptx::smem_u32(xbuf + ((size_t)par * C + rank) * E);
-          for (int e = tid; e < E; e += NCT) {
-            float acc = 0.f;
+        if (C > 1 && tid == 0) ptx::mbar_arrive_expect_tx(&xfull[par], (uint32_t)C * E * 4);
+        named_sync(BAR_COMPUTE, NCT);
+        {
+          // sum the NSLOT warp partials (float4 = 4 consecutive lanes) and publish the CTA partial:
+          // locally for C == 1, else into every peer's xbuf[par][rank] with st.async
+          float* mine = xbuf + ((size_t)par * C + rank) * E;
+          const uint32_t mine_a = ptx::smem_u32(mine);
+          const uint32_t bar_a = ptx::smem_u32(&xfull[par]);
+          for (int e4 = tid; e4 < E / 4; e4 += NCT) {
+            float4 acc = reinterpret_cast<const float4*>(red)[e4];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) acc += red[w * E + e];
-            for (int r = 0; r < C; ++r) st_cluster_f32(map_to_rank(xb + e * 4, r), acc);
-          }
-          fence_cluster();
-          __syncwarp();
-          if (lane == 0) {
-            const uint32_t bar = ptx::smem_u32(&xfull[par]);
-            for (int r = 0; r < C; ++r) mbar_arrive_remote(map_to_rank(bar, r));
-          }
-          while (!mbar_try_wait_cluster(&xfull[par], (npass >> 1) & 1)) {
-          }
-          named_sync(BAR_COMPUTE, NCT);  // everybody is done reading red[] partials
-          for (int e = tid; e < E; e += NCT) {
-            float acc = 0.f;
-            for (int r = 0; r < C; ++r) acc += xbuf[((size_t)par * C + r) * E + e];
-            red[e] = acc;
-          }
-        } else {
-          float acc[(E + NCT - 1) / NCT];
-#pragma unroll
-          for (int m = 0; m < (E + NCT - 1) / NCT; ++m) {
-            const int e = tid + m * NCT;
-            acc[m] = 0.f;
-            if (e < E) {
-#pragma unroll
-              for (int w = 0; w < NW; ++w) acc[m] += red[w * E + e];
+            for (int w = 1; w < NSLOT; ++w) {
+              const float4 x = reinterpret_cast<const float4*>(red + w * E)[e4];
+              acc.x += x.x;
+              acc.y += x.y;
+              acc.z += x.z;
+              acc.w += x.w;
+            }
+            if (C > 1) {
+              for (int r = 0; r < C; ++r)
+                st_async_v4(map_to_rank(mine_a + e4 * 16, r), acc, map_to_rank(bar_a, r));
+            } else {
+              reinterpret_cast<float4*>(mine)[e4] = acc;
             }
           }
+        }
+        if (C > 1) {
+          ptx::mbar_wait(&xfull[par], (npass >> 1) & 1);
+        } else {
           named_sync(BAR_COMPUTE, NCT);
-#pragma unroll
-          for (int m = 0; m < (E + NCT - 1) / NCT; ++m) {
-            const int e = tid + m * NCT;
-            if (e < E) red[e] = acc[m];
-          }
         }
         ++npass;
-        named_sync(BAR_COMPUTE, NCT);
 
-        // ---- squash (naive:248-253), Vacc update, hand v to the output warps ------------------
-        if (last_pass && s >= 2) named_sync(BAR_FREE0 + (s & 1), NSYNC);
+        // ---- cluster sum + squash (naive:248-253), Vacc update, hand v to the output warps ----
         if (tid < 2 * OPL * 32) {
-          const int fq = tid >> 5;
+          // vout[s&1] was last used by frame s-2: wait until both output warps have read it
+          if (last_pass && s >= 2) ptx::mbar_wait(&vfree[s & 1], ((s >> 1) - 1) & 1);
+          const int fq = tid >> 5;  // f*OPL + q
+          const float* xb = xbuf + (size_t)par * C * E + (size_t)fq * T * 32 + lane;
           float t[T];
           float n2 = 0.f;
 #pragma unroll
           for (int k = 0; k < T; ++k) {
-            t[k] = red[(fq * T + k) * 32 + lane];
-            n2 = fmaf(t[k], t[k], n2);
+            float acc = xb[k * 32];
+            for (int r = 1; r < C; ++r) acc += xb[(size_t)r * E + k * 32];
+            t[k] = acc;
+            n2 = fmaf(acc, acc, n2);
           }
           const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
           float* vo = vout + (size_t)(s & 1) * E;
@@ -324,12 +372,12 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
           }
         }
         named_sync(BAR_COMPUTE, NCT);
-        if (last_pass) named_arrive(BAR_READY0 + (s & 1), NSYNC);
+        if (last_pass && tid == 0) ptx::mbar_arrive(&vready[s & 1]);
       }
     }
-  } else if (warp <= NW + 2) {
+  } else if (warp <= NCW + 2) {
     // ============================== output warps (one per pair member) ==============================
-    const int f = warp - (NW + 1);
+    const int f = warp - (NCW + 1);
     const bool do_ln = p.ln_gamma != nullptr;
     const bool do_head = p.head_gamma != nullptr;
     float gam[OPL][T], bet[OPL][T], hg[OPL], hb[OPL];
@@ -347,14 +395,15 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
     }
     const float inv_n = 1.0f / (float)(O * D);
     for (int s = 0; s < p.nsteps; ++s) {
-      named_sync(BAR_READY0 + (s & 1), NSYNC);
-      const float* vf = vout + (size_t)(s & 1) * E + (size_t)f * OPL * T * 32;
+      ptx::mbar_wait(&vready[s & 1], (s >> 1) & 1);
+      const float* vf = vout + (size_t)(s & 1) * E + (size_t)f * EF;
       float y[OPL][T];
 #pragma unroll
       for (int q = 0; q < OPL; ++q)
 #pragma unroll
         for (int k = 0; k < T; ++k) y[q][k] = vf[(q * T + k) * 32 + lane];
-      if (s + 2 < p.nsteps) named_arrive(BAR_FREE0 + (s & 1), NSYNC);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&vfree[s & 1]);
 
       long long frame;
       bool ok;
@@ -437,16 +486,16 @@ __global__ void __launch_bounds__((NW + 3) * 32, 1) route_stream_kernel(const Ro
 }
 
 // ---------------------------------------------------------------------------------------
-template <int T, int OPL, bool BF16>
+template <int T, int OPL, int FPW, bool BF16>
 static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_t smem_bytes,
                                          cudaStream_t stream) {
-  auto kern = route_stream_kernel<T, OPL, SRF_NW, BF16>;
+  auto kern = route_stream_kernel<T, OPL, SRF_NW, FPW, BF16>;
   cudaError_t err =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * p.C));
-  cfg.blockDim = dim3((SRF_NW + 3) * 32);
+  cfg.blockDim = dim3((SRF_NW * (2 / FPW) + 3) * 32);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -463,27 +512,28 @@ static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_
 size_t route_stream_fixed_smem(int T, int OPL, int C, int max_stages) {
   const size_t E = (size_t)2 * OPL * T * 32;
   return sizeof(float) * ((size_t)SRF_NW * E + (size_t)2 * C * E + 3 * E) +
-         sizeof(uint64_t) * (2 * (size_t)max_stages + 2) + 128;
+         sizeof(uint64_t) * (2 * (size_t)max_stages + 6) + 128;
 }
 size_t route_stream_stage_bytes(int T, int OPL, bool bf16) {
   return (size_t)SRF_NW * OPL * (T / 4) * 128 * 2 * (bf16 ? 2 : 4);
 }
 
-#define SRF_STREAM(T_, OPL_)                                                            \
-  if (T == T_ && OPL == OPL_)                                                           \
-    return bf16 ? launch_stream_variant<T_, OPL_, true>(p, groups, smem_bytes, stream)  \
-                : launch_stream_variant<T_, OPL_, false>(p, groups, smem_bytes, stream);
+// variants with a per-lane state of <= 20 floats per pair member run one member per warp
+#define SRF_STREAM(T_, OPL_, FPW_)                                                            \
+  if (T == T_ && OPL == OPL_)                                                                 \
+    return bf16 ? launch_stream_variant<T_, OPL_, FPW_, true>(p, groups, smem_bytes, stream)  \
+                : launch_stream_variant<T_, OPL_, FPW_, false>(p, groups, smem_bytes, stream);
 
 cudaError_t launch_route_stream(const RouteParams& p, int T, int OPL, bool bf16, int groups,
                                 size_t smem_bytes, cudaStream_t stream) {
-  SRF_STREAM(8, 1)
-  SRF_STREAM(8, 2)
-  SRF_STREAM(8, 4)
-  SRF_STREAM(16, 1)
-  SRF_STREAM(16, 2)
-  SRF_STREAM(20, 1)
-  SRF_STREAM(20, 2)
-  SRF_STREAM(32, 1)
+  SRF_STREAM(8, 1, 1)
+  SRF_STREAM(8, 2, 1)
+  SRF_STREAM(8, 4, 2)
+  SRF_STREAM(16, 1, 1)
+  SRF_STREAM(16, 2, 2)
+  SRF_STREAM(20, 1, 1)
+  SRF_STREAM(20, 2, 2)
+  SRF_STREAM(32, 1, 2)
   return cudaErrorInvalidValue;
 }
 

@@ -16,10 +16,11 @@
 //   * W[i] arrives with one 1-D bulk copy (pre-packed in the shared-memory image order);
 //   * tcgen05.mma kind::tf32 reads the fp32 tiles directly (TF32 truncation in the tensor core),
 //     M=128, N=64, K=8 per instruction, fp32 accumulators in TMEM (8 slots of 64 columns);
-//   * 4 epilogue warps drain TMEM with tcgen05.ld, add the bias and store u_hat in the layout
+//   * 8 epilogue warps drain TMEM with tcgen05.ld, add the bias and store u_hat in the layout
 //     the routing kernel streams: [frame pair][i][M tile][row][2] (bf16 or fp32), 128 contiguous
 //     bytes per warp store.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..9 = epilogue
+// (two per TMEM lane quarter, 32 of the 64 columns each).
 // Pipelines: x tiles (XSTAGES-deep mbarrier ring), W tile (single buffer, full/empty), TMEM slots
 // (8-deep full/empty ring between the MMA issuer and the epilogue).
 
@@ -88,7 +89,8 @@ void launch_pack_weights_mma(const float* W, const float* bias, float* Wm, float
 constexpr int UH_N = 64;         // frames per MMA (TMEM columns per slot)
 constexpr int UH_SLOTS = 8;      // 8 x 64 = 512 TMEM columns
 constexpr int UH_XSTAGES = 4;    // x-tile ring depth
-constexpr int UH_THREADS = 192;  // 6 warps
+constexpr int UH_EPI_WARPS = 8;   // 2 per TMEM lane quarter, 32 columns each
+constexpr int UH_THREADS = (2 + UH_EPI_WARPS) * 32;
 
 __global__ void __launch_bounds__(UH_THREADS, 1)
 uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p) {
@@ -122,7 +124,7 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     }
     for (int s = 0; s < UH_SLOTS; ++s) {
       ptx::mbar_init(&t_full[s], 1);
-      ptx::mbar_init(&t_empty[s], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&t_empty[s], UH_EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::mbar_init(w_full, 1);
     ptx::mbar_init(w_empty, 1);
@@ -205,46 +207,57 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     }
   } else {
     // ================= epilogue: TMEM -> (+bias) -> u_hat in HBM =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int ch0 = ((warp - 2) >> 2);  // which 32-column half of the slot
     const int row = q * 32 + lane;
     uint32_t n_t = 0;
     const int halfB = p.Bpad >> 1;
+    const int lgNB = 31 - __clz(p.NB);  // NB is a power of two
+    const size_t gstride = (size_t)p.I * MT * 256;  // elements between consecutive frame pairs
     for (long long item = item_lo; item < item_hi; ++item) {
       const int i = (int)(item / ntiles), tile = (int)(item % ntiles);
       const int b0 = (tile % p.NBT) * p.NB, s0 = (tile / p.NBT) * p.NS;
+      // frame-pair index and validity of the 16 column pairs this warp owns (n = ch0*32 + 2*pr)
+      long long gofs[16];
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int pr = 0; pr < 16; ++pr) {
+        const int n = ch0 * 32 + pr * 2;
+        const int s = s0 + (n >> lgNB), b = b0 + (n & (p.NB - 1));
+        gofs[pr] = ((long long)s * halfB + (b >> 1)) * (long long)gstride;
+        if (s < p.S && b < p.B) okmask |= 1u << pr;
+      }
       for (int mt = 0; mt < MT; ++mt) {
         const int slot = n_t % UH_SLOTS;
         const float bias = __ldg(p.Bm + ((size_t)i * MT + mt) * 128 + row);
+        const size_t rowofs = (((size_t)i * MT + mt) * 128 + row) * 2;
         ptx::mbar_wait(&t_full[slot], (n_t / UH_SLOTS) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * UH_N;
-#pragma unroll
-        for (int ch = 0; ch < UH_N / 16; ++ch) {
-          uint32_t r[16];
-          ptx::tmem_ld16(taddr + ch * 16, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int pr = 0; pr < 8; ++pr) {
-            const int n = ch * 16 + pr * 2;
-            const int s = s0 + n / p.NB, b = b0 + n % p.NB;
-            if (s < p.S && b < p.B) {
-              const long long g = (long long)s * halfB + (b >> 1);
-              const size_t e = ((((size_t)g * p.I + i) * MT + mt) * 128 + row) * 2;
-              const float v0 = __uint_as_float(r[pr * 2]) + bias;
-              const float v1 = __uint_as_float(r[pr * 2 + 1]) + bias;
-              if (p.store_bf16) {
-                *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.u) + e) =
-                    __floats2bfloat162_rn(v0, v1);
-              } else {
-                *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.u) + e) = make_float2(v0, v1);
-              }
-            }
-          }
-        }
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * UH_N + (uint32_t)ch0 * 32;
+        uint32_t r0[16], r1[16];
+        ptx::tmem_ld16(taddr, r0);
+        ptx::tmem_ld16(taddr + 16, r1);
+        ptx::tmem_ld_wait();
+        // the slot can be refilled as soon as its values sit in registers
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[slot]);
         ++n_t;
+#pragma unroll
+        for (int pr = 0; pr < 16; ++pr) {
+          if (okmask & (1u << pr)) {
+            const float v0 = __uint_as_float(pr < 8 ? r0[pr * 2] : r1[(pr - 8) * 2]) + bias;
+            const float v1 = __uint_as_float(pr < 8 ? r0[pr * 2 + 1] : r1[(pr - 8) * 2 + 1]) + bias;
+            const size_t e = (size_t)gofs[pr] + rowofs;
+            if (p.store_bf16) {
+              *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.u) + e) =
+                  __floats2bfloat162_rn(v0, v1);
+            } else {
+              *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.u) + e) = make_float2(v0, v1);
+            }
+          }
+        }
       }
     }
   }

@@ -140,12 +140,11 @@ route_stream_kernel(const RouteParams p) {
     ptx::mbar_init(&xfull[0], 1);
     ptx::mbar_init(&xfull[1], 1);
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&vready[b], 1);
+      ptx::mbar_init(&vready[b], 2 / FPW);  // one arrive per slot-0 consumer warp
       ptx::mbar_init(&vfree[b], 2);  // one arrive per output warp
     }
     ptx::fence_barrier_init();
   }
-  for (int e = tid; e < E; e += blockDim.x) vacc[e] = 0.f;
   __syncthreads();
   if (C > 1) cluster_sync_all();  // peers' barriers are initialised before anybody pushes
 
@@ -181,19 +180,25 @@ route_stream_kernel(const RouteParams p) {
     int st = 0;
     uint32_t ph = 0;
     uint32_t npass = 0;   // exchange counter
+    // Vacc = sum of the squashed outputs the logits are linear in (previous frame's output for
+    // SDR) -- kept in registers across passes and frames; lane = output capsule.
+    float va[FPW][OPL][T];
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+#pragma unroll
+      for (int q = 0; q < OPL; ++q)
+#pragma unroll
+        for (int k = 0; k < T; ++k) va[f][q][k] = 0.f;
     for (int s = 0; s < p.nsteps; ++s) {
       for (int pass = 0; pass < p.iters; ++pass) {
         const bool last_pass = pass == p.iters - 1;
-        float va[FPW][OPL][T], ta[FPW][OPL][T];
+        float ta[FPW][OPL][T];
 #pragma unroll
         for (int f = 0; f < FPW; ++f)
 #pragma unroll
           for (int q = 0; q < OPL; ++q)
 #pragma unroll
-            for (int k = 0; k < T; ++k) {
-              va[f][q][k] = vacc[(f0 + f) * EF + (q * T + k) * 32 + lane];
-              ta[f][q][k] = 0.f;
-            }
+            for (int k = 0; k < T; ++k) ta[f][q][k] = 0.f;
 
         for (int base = i_lo; base < i_hi; base += NSLOT) {
           const int i = base + slot;
@@ -342,37 +347,43 @@ route_stream_kernel(const RouteParams p) {
         }
         ++npass;
 
-        // ---- cluster sum + squash (naive:248-253), Vacc update, hand v to the output warps ----
-        if (tid < 2 * OPL * 32) {
-          // vout[s&1] was last used by frame s-2: wait until both output warps have read it
-          if (last_pass && s >= 2) ptx::mbar_wait(&vfree[s & 1], ((s >> 1) - 1) & 1);
-          const int fq = tid >> 5;  // f*OPL + q
-          const float* xb = xbuf + (size_t)par * C * E + (size_t)fq * T * 32 + lane;
-          float t[T];
-          float n2 = 0.f;
+        // ---- cluster sum + squash (naive:248-253) + Vacc update ------------------------------
+        // every consumer warp does this for its own (member, lane) columns: the result feeds
+        // its registers directly, so no barrier separates the passes; the slot-0 warps also
+        // hand v to the output warps.
+        const bool writer = last_pass && slot == 0;
+        if (writer && s >= 2) ptx::mbar_wait(&vfree[s & 1], ((s >> 1) - 1) & 1);
 #pragma unroll
-          for (int k = 0; k < T; ++k) {
-            float acc = xb[k * 32];
-            for (int r = 1; r < C; ++r) acc += xb[(size_t)r * E + k * 32];
-            t[k] = acc;
-            n2 = fmaf(acc, acc, n2);
-          }
-          const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
-          float* vo = vout + (size_t)(s & 1) * E;
+        for (int f = 0; f < FPW; ++f)
 #pragma unroll
-          for (int k = 0; k < T; ++k) {
-            const int e = (fq * T + k) * 32 + lane;
-            const float v = t[k] * scale;
-            if (last_pass) {
-              vo[e] = v;
-              vacc[e] = p.sdr ? v : 0.f;  // SDR: next frame starts from this output (naive:167)
-            } else {
-              vacc[e] += v;
+          for (int q = 0; q < OPL; ++q) {
+            const float* xb = xbuf + (size_t)par * C * E + (size_t)(f0 + f) * EF + q * T * 32 + lane;
+            float t[T];
+            float n2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+              float acc = xb[k * 32];
+              for (int r = 1; r < C; ++r) acc += xb[(size_t)r * E + k * 32];
+              t[k] = acc;
+              n2 = fmaf(acc, acc, n2);
+            }
+            const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
+            float* vo = vout + (size_t)(s & 1) * E + (size_t)(f0 + f) * EF + q * T * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+              const float v = t[k] * scale;
+              if (last_pass) {
+                if (writer) vo[k * 32] = v;
+                va[f][q][k] = p.sdr ? v : 0.f;  // SDR: next frame starts from this output (naive:167)
+              } else {
+                va[f][q][k] += v;
+              }
             }
           }
+        if (writer) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&vready[s & 1]);
         }
-        named_sync(BAR_COMPUTE, NCT);
-        if (last_pass && tid == 0) ptx::mbar_arrive(&vready[s & 1]);
       }
     }
   } else if (warp <= NCW + 2) {

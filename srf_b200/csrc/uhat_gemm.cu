@@ -92,6 +92,7 @@ constexpr int UH_XSTAGES = 4;    // x-tile ring depth
 constexpr int UH_EPI_WARPS = 8;   // 2 per TMEM lane quarter, 32 columns each
 constexpr int UH_THREADS = (2 + UH_EPI_WARPS) * 32;
 
+template <bool BF16>
 __global__ void __launch_bounds__(UH_THREADS, 1)
 uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -213,24 +214,27 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     uint32_t n_t = 0;
     const int halfB = p.Bpad >> 1;
     const int lgNB = 31 - __clz(p.NB);  // NB is a power of two
-    const size_t gstride = (size_t)p.I * MT * 256;  // elements between consecutive frame pairs
+    constexpr int ES = BF16 ? 2 : 4;    // bytes per stored element
+    const long long gstride = (long long)p.I * MT * 256 * ES;  // bytes between frame pairs
+    uint8_t* const ubytes = reinterpret_cast<uint8_t*>(p.u);
     for (long long item = item_lo; item < item_hi; ++item) {
       const int i = (int)(item / ntiles), tile = (int)(item % ntiles);
       const int b0 = (tile % p.NBT) * p.NB, s0 = (tile / p.NBT) * p.NS;
-      // frame-pair index and validity of the 16 column pairs this warp owns (n = ch0*32 + 2*pr)
+      // byte offset of the frame pair and validity of the 16 column pairs this warp owns
       long long gofs[16];
       uint32_t okmask = 0;
 #pragma unroll
       for (int pr = 0; pr < 16; ++pr) {
         const int n = ch0 * 32 + pr * 2;
         const int s = s0 + (n >> lgNB), b = b0 + (n & (p.NB - 1));
-        gofs[pr] = ((long long)s * halfB + (b >> 1)) * (long long)gstride;
+        gofs[pr] = ((long long)s * halfB + (b >> 1)) * gstride;
         if (s < p.S && b < p.B) okmask |= 1u << pr;
       }
+      const bool all_ok = okmask == 0xffffu;
       for (int mt = 0; mt < MT; ++mt) {
         const int slot = n_t % UH_SLOTS;
         const float bias = __ldg(p.Bm + ((size_t)i * MT + mt) * 128 + row);
-        const size_t rowofs = (((size_t)i * MT + mt) * 128 + row) * 2;
+        uint8_t* const prow = ubytes + (((size_t)i * MT + mt) * 128 + row) * 2 * ES;
         ptx::mbar_wait(&t_full[slot], (n_t / UH_SLOTS) & 1);
         ptx::tc_fence_after();
         const uint32_t taddr =
@@ -244,17 +248,26 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[slot]);
         ++n_t;
+        if (all_ok) {
 #pragma unroll
-        for (int pr = 0; pr < 16; ++pr) {
-          if (okmask & (1u << pr)) {
+          for (int pr = 0; pr < 16; ++pr) {
             const float v0 = __uint_as_float(pr < 8 ? r0[pr * 2] : r1[(pr - 8) * 2]) + bias;
             const float v1 = __uint_as_float(pr < 8 ? r0[pr * 2 + 1] : r1[(pr - 8) * 2 + 1]) + bias;
-            const size_t e = (size_t)gofs[pr] + rowofs;
-            if (p.store_bf16) {
-              *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.u) + e) =
-                  __floats2bfloat162_rn(v0, v1);
-            } else {
-              *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.u) + e) = make_float2(v0, v1);
+            if (BF16)
+              *reinterpret_cast<__nv_bfloat162*>(prow + gofs[pr]) = __floats2bfloat162_rn(v0, v1);
+            else
+              *reinterpret_cast<float2*>(prow + gofs[pr]) = make_float2(v0, v1);
+          }
+        } else {
+#pragma unroll
+          for (int pr = 0; pr < 16; ++pr) {
+            if (okmask & (1u << pr)) {
+              const float v0 = __uint_as_float(pr < 8 ? r0[pr * 2] : r1[(pr - 8) * 2]) + bias;
+              const float v1 = __uint_as_float(pr < 8 ? r0[pr * 2 + 1] : r1[(pr - 8) * 2 + 1]) + bias;
+              if (BF16)
+                *reinterpret_cast<__nv_bfloat162*>(prow + gofs[pr]) = __floats2bfloat162_rn(v0, v1);
+              else
+                *reinterpret_cast<float2*>(prow + gofs[pr]) = make_float2(v0, v1);
             }
           }
         }
@@ -278,12 +291,12 @@ size_t uhat_gemm_smem_bytes(int MT, int KC) {
 cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int num_sms,
                              cudaStream_t stream) {
   const size_t smem = uhat_gemm_smem_bytes(p.MT, p.KC);
-  cudaError_t e = cudaFuncSetAttribute(uhat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  auto kern = p.store_bf16 ? uhat_gemm_kernel<true> : uhat_gemm_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long grid = p.items < num_sms ? p.items : num_sms;
   if (grid < 1) grid = 1;
-  uhat_gemm_kernel<<<(unsigned)grid, UH_THREADS, smem, stream>>>(tmap, p);
+  kern<<<(unsigned)grid, UH_THREADS, smem, stream>>>(tmap, p);
   return cudaGetLastError();
 }
 

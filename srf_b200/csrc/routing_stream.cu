@@ -124,8 +124,8 @@ route_stream_kernel(const RouteParams p) {
   uint8_t* ring = smem_raw;                                        // [NSTAGE][STAGE]
   float* red = reinterpret_cast<float*>(ring + (size_t)NSTAGE * STAGE);  // [NSLOT][E] warp partials
   float* xbuf = red + NSLOT * E;                                   // [2][C][E] CTA partial sums
-  float* vacc = xbuf + 2 * C * E;                                  // [E]
-  float* vout = vacc + E;                                          // [2][E]
+  float* tot = xbuf + 2 * C * E;                                   // [E] cluster-summed t
+  float* vout = tot + E;                                           // [2][E]
   uint64_t* full = reinterpret_cast<uint64_t*>(vout + 2 * E);      // [NSTAGE]
   uint64_t* empty = full + NSTAGE;                                 // [NSTAGE]
   uint64_t* xfull = empty + NSTAGE;                                // [2]
@@ -177,6 +177,7 @@ route_stream_kernel(const RouteParams p) {
     // ============================== consumers ==============================
     const int slot = FPW == 1 ? (warp >> 1) : warp;   // capsule slot inside a stage
     const int f0 = FPW == 1 ? (warp & 1) : 0;         // first pair member of this warp
+    const uint32_t ushift = f0 ? 0u : 16u;            // bf16 member select: (w << ushift) & 0xffff0000
     int st = 0;
     uint32_t ph = 0;
     uint32_t npass = 0;   // exchange counter
@@ -229,13 +230,12 @@ route_stream_kernel(const RouteParams p) {
                 const uint32_t w[4] = {raw[m].x, raw[m].y, raw[m].z, raw[m].w};
 #pragma unroll
                 for (int kin = 0; kin < 4; ++kin) {
-                  const float lo = __uint_as_float(w[kin] << 16);
-                  const float hi = __uint_as_float(w[kin] & 0xffff0000u);
                   if (FPW == 2) {
-                    u[0][q][k4 * 4 + kin] = lo;
-                    u[FPW - 1][q][k4 * 4 + kin] = hi;
+                    u[0][q][k4 * 4 + kin] = __uint_as_float(w[kin] << 16);
+                    u[FPW - 1][q][k4 * 4 + kin] = __uint_as_float(w[kin] & 0xffff0000u);
                   } else {
-                    u[0][q][k4 * 4 + kin] = f0 ? hi : lo;
+                    // member 0 = low half (<< 16), member 1 = high half (mask): one LOP3/SHF each
+                    u[0][q][k4 * 4 + kin] = __uint_as_float((w[kin] << ushift) & 0xffff0000u);
                   }
                 }
               } else {
@@ -347,9 +347,25 @@ route_stream_kernel(const RouteParams p) {
         }
         ++npass;
 
-        // ---- cluster sum + squash (naive:248-253) + Vacc update ------------------------------
-        // every consumer warp does this for its own (member, lane) columns: the result feeds
-        // its registers directly, so no barrier separates the passes; the slot-0 warps also
+        // ---- cluster sum (cooperative, float4) -> tot[0..E) ------------------------------------
+        if (C > 1) {
+          const float4* xb4 = reinterpret_cast<const float4*>(xbuf + (size_t)par * C * E);
+          for (int e4 = tid; e4 < E / 4; e4 += NCT) {
+            float4 acc = xb4[e4];
+            for (int r = 1; r < C; ++r) {
+              const float4 x = xb4[(size_t)r * (E / 4) + e4];
+              acc.x += x.x;
+              acc.y += x.y;
+              acc.z += x.z;
+              acc.w += x.w;
+            }
+            reinterpret_cast<float4*>(tot)[e4] = acc;
+          }
+          named_sync(BAR_COMPUTE, NCT);
+        }
+        const float* total = C > 1 ? tot : xbuf + (size_t)par * E;
+        // ---- squash (naive:248-253) + Vacc update: every consumer warp does this for its own
+        // (member, lane) columns, the result feeds its registers directly; the slot-0 warps also
         // hand v to the output warps.
         const bool writer = last_pass && slot == 0;
         if (writer && s >= 2) ptx::mbar_wait(&vfree[s & 1], ((s >> 1) - 1) & 1);
@@ -357,15 +373,13 @@ route_stream_kernel(const RouteParams p) {
         for (int f = 0; f < FPW; ++f)
 #pragma unroll
           for (int q = 0; q < OPL; ++q) {
-            const float* xb = xbuf + (size_t)par * C * E + (size_t)(f0 + f) * EF + q * T * 32 + lane;
+            const float* xb = total + (size_t)(f0 + f) * EF + q * T * 32 + lane;
             float t[T];
             float n2 = 0.f;
 #pragma unroll
             for (int k = 0; k < T; ++k) {
-              float acc = xb[k * 32];
-              for (int r = 1; r < C; ++r) acc += xb[(size_t)r * E + k * 32];
-              t[k] = acc;
-              n2 = fmaf(acc, acc, n2);
+              t[k] = xb[k * 32];
+              n2 = fmaf(t[k], t[k], n2);
             }
             const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
             float* vo = vout + (size_t)(s & 1) * E + (size_t)(f0 + f) * EF + q * T * 32 + lane;

@@ -111,6 +111,16 @@ int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, int32_t n_l
  */
 int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* layer, float* out_uhat, void* stream);
 
+/*
+ * per-kernel device timing (measurement aid for bench.py): between srf_profile_begin and
+ * srf_profile_end every kernel the handle launches is bracketed by CUDA events on its launch
+ * stream.  srf_profile_end synchronises those events and returns, per kernel kind
+ * (0 = weight packing, 1 = u_hat GEMM, 2 = routing kernel), the summed milliseconds and the
+ * number of launches in ms[3] / launches[3] (host arrays).
+ */
+int srf_profile_begin(srf_handle* h);
+int srf_profile_end(srf_handle* h, float* ms, int32_t* launches);
+
 /* number of kernels this library has launched through the handle since creation
  * (bench.py's gpu_launches claim is read from here) */
 int64_t srf_launch_count(const srf_handle* h);

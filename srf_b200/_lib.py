@@ -14,7 +14,8 @@ UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF1
 
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",
-           "srf_route_stack_fwd", "srf_uhat_fwd", "srf_launch_count", "srf_last_kernel")
+           "srf_route_stack_fwd", "srf_uhat_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
+           "srf_last_kernel")
 
 
 class LayerDesc(Structure):
@@ -56,6 +57,10 @@ def load() -> ctypes.CDLL:
   lib.srf_route_stack_fwd.restype = c_int
   lib.srf_uhat_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_void_p, c_void_p]
   lib.srf_uhat_fwd.restype = c_int
+  lib.srf_profile_begin.argtypes = [c_void_p]
+  lib.srf_profile_begin.restype = c_int
+  lib.srf_profile_end.argtypes = [c_void_p, POINTER(c_float), POINTER(c_int32)]
+  lib.srf_profile_end.restype = c_int
   lib.srf_launch_count.argtypes = [c_void_p]
   lib.srf_launch_count.restype = c_int64
   lib.srf_last_kernel.argtypes = [c_void_p]

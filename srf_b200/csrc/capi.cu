@@ -44,7 +44,35 @@ struct srf_handle {
   void* ubuf = nullptr;  // materialised u_hat of one layer
   size_t ubuf_bytes = 0;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled
+  // per-kernel timing (srf_profile_begin/end)
+  bool profiling = false;
+  struct Span {
+    int kind;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;
 };
+
+namespace {
+// brackets one kernel launch with events when profiling is on
+struct KernelSpan {
+  srf_handle* h;
+  cudaStream_t stream;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  KernelSpan(srf_handle* h_, int kind_, cudaStream_t s) : h(h_), stream(s), kind(kind_) {
+    if (!h->profiling) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, stream);
+  }
+  ~KernelSpan() {
+    if (!a) return;
+    cudaEventRecord(b, stream);
+    h->spans.push_back({kind, a, b});
+  }
+};
+}  // namespace
 
 static std::string g_create_error;
 
@@ -130,6 +158,43 @@ extern "C" const char* srf_last_error(const srf_handle* h) {
   return h ? h->error.c_str() : g_create_error.c_str();
 }
 
+extern "C" int srf_profile_begin(srf_handle* h) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  for (auto& sp : h->spans) {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  h->spans.clear();
+  h->profiling = true;
+  return 0;
+}
+
+extern "C" int srf_profile_end(srf_handle* h, float* ms, int32_t* launches) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (!ms || !launches) return fail(h, -1, "ms / launches is NULL");
+  DeviceGuard g(h->device);
+  h->profiling = false;
+  for (int k = 0; k < 3; ++k) {
+    ms[k] = 0.f;
+    launches[k] = 0;
+  }
+  int rc = 0;
+  for (auto& sp : h->spans) {
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, sp.a, sp.b);
+    if (e != cudaSuccess && rc == 0) rc = cuda_fail(h, e, "srf_profile_end");
+    if (sp.kind >= 0 && sp.kind < 3) {
+      ms[sp.kind] += t;
+      launches[sp.kind]++;
+    }
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  h->spans.clear();
+  return rc;
+}
+
 extern "C" int64_t srf_launch_count(const srf_handle* h) { return h ? h->launches : 0; }
 
 extern "C" const char* srf_last_kernel(const srf_handle* h) {
@@ -205,7 +270,10 @@ static int get_packed(srf_handle* h, const srf_layer_desc* L, int I, int T, int 
   hit->T = T;
   hit->OP = OP;
   hit->version = L->weights_version;
-  srf::launch_pack_weights(L->W, L->bias, hit->Wp, hit->Bp, I, L->O, L->D, L->d, T, OP, stream);
+  {
+    KernelSpan span(h, 0, stream);
+    srf::launch_pack_weights(L->W, L->bias, hit->Wp, hit->Bp, I, L->O, L->D, L->d, T, OP, stream);
+  }
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, "pack_weights launch");
@@ -300,8 +368,11 @@ static int get_packed_mma(srf_handle* h, const srf_layer_desc* L, const UhatGeom
   hit->D = L->D;
   hit->d = L->d;
   hit->version = L->weights_version;
-  srf::launch_pack_weights_mma(L->W, L->bias, hit->Wp, hit->Bp, g.I, L->O, L->D, L->d, g.T, g.OPL,
-                               g.KC, stream);
+  {
+    KernelSpan span(h, 0, stream);
+    srf::launch_pack_weights_mma(L->W, L->bias, hit->Wp, hit->Bp, g.I, L->O, L->D, L->d, g.T, g.OPL,
+                                 g.KC, stream);
+  }
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, "pack_weights_mma launch");
@@ -364,7 +435,11 @@ static int compute_uhat(srf_handle* h, const srf_layer_desc* L, const UhatGeom& 
   p.Bpad = g.Bpad;
   p.store_bf16 = g.bf16 ? 1 : 0;
   p.items = (long long)g.I * g.NBT * g.NST;
-  cudaError_t e = srf::launch_uhat_gemm(tmap, p, h->num_sms, stream);
+  cudaError_t e;
+  {
+    KernelSpan span(h, 1, stream);
+    e = srf::launch_uhat_gemm(tmap, p, h->num_sms, stream);
+  }
   if (e != cudaSuccess) return cuda_fail(h, e, "uhat_gemm launch");
   h->launches++;
   return 0;
@@ -509,7 +584,11 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
       p.Ic = (I + Cs - 1) / Cs;
       p.nstage = nstage;
       const size_t smem_s = fixed + (size_t)nstage * stage;
-      cudaError_t es = srf::launch_route_stream(p, T, OPL, um == 1, groups, smem_s, stream);
+      cudaError_t es;
+      {
+        KernelSpan span(h, 2, stream);
+        es = srf::launch_route_stream(p, T, OPL, um == 1, groups, smem_s, stream);
+      }
       if (es != cudaSuccess) {
         cudaGetLastError();
         return cuda_fail(h, es, "route_stream launch");
@@ -525,7 +604,11 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
     }
   }
 
-  cudaError_t e = srf::launch_route_layer(p, T, OPL, F, groups, smem, um, stream);
+  cudaError_t e;
+  {
+    KernelSpan span(h, 2, stream);
+    e = srf::launch_route_layer(p, T, OPL, F, groups, smem, um, stream);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     return cuda_fail(h, e, "route_layer launch");

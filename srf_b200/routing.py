@@ -63,6 +63,16 @@ class Handle:
     except Exception:  # pylint: disable=broad-except
       pass
 
+  def profile_begin(self):
+    _lib.check(self.lib, self._h, self.lib.srf_profile_begin(self._h), "srf_profile_begin")
+
+  def profile_end(self):
+    """-> {"pack": (ms, launches), "uhat_gemm": (...), "routing": (...)} since profile_begin."""
+    ms = (ctypes.c_float * 3)()
+    n = (ctypes.c_int32 * 3)()
+    _lib.check(self.lib, self._h, self.lib.srf_profile_end(self._h, ms, n), "srf_profile_end")
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("pack", "uhat_gemm", "routing"))}
+
   @property
   def launches(self) -> int:
     return int(self.lib.srf_launch_count(self._h))

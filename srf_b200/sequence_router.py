@@ -126,3 +126,170 @@ class RoutingStack:
                                    return_capsules=return_capsules, out_logits=out_logits)
 
   __call__ = forward
+
+
+# ----------------------------------------------------------------------------------------
+# Drop-in model class
+# ----------------------------------------------------------------------------------------
+def _conv2d_same_nhwc(x, kernel, bias, stride):
+  """Keras Conv2D(padding='same') on NHWC input with a TF-layout kernel [kh,kw,cin,cout]:
+  out = ceil(in/stride), pad_total = max((out-1)*stride + k - in, 0), pad_before = pad_total//2."""
+  import torch.nn.functional as F
+  B, H, W, _ = x.shape
+  k = kernel.shape[0]
+  oh, ow = -(-H // stride), -(-W // stride)
+  ph, pw = max((oh - 1) * stride + k - H, 0), max((ow - 1) * stride + k - W, 0)
+  xp = F.pad(x.permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+  y = F.conv2d(xp, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=stride)
+  return y.permute(0, 2, 3, 1)
+
+
+def _feat_mask(x, lengths, div):
+  """tfsr/helper/model_helper.py:125-140: zero the frames at or beyond ceil(len / div)."""
+  n = torch.ceil(lengths.to(torch.float32) / div).to(torch.int64)
+  mask = (torch.arange(x.shape[1], device=x.device)[None, :] < n[:, None]).to(x.dtype)
+  return x * mask[:, :, None, None]
+
+
+class SequenceRouter:
+  """Drop-in for tfsr.model.sequence_router_naive.SequenceRouter (naive:33-193): same
+  constructor `(config, logger, class_n)`, same call `model(inputs, input_lengths=...,
+  training=...)` -> logits [B, ceil(T/4), class_n] (ignored extra kwargs such as `mask`,
+  `att_mask` are accepted, utils/average_ckpt_sr.py:127-128).
+
+  The routing stack (naive:145-193) -- the hot path -- runs in the CUDA library.  The
+  capsulation front-end (naive:129-142, sequence_router.py:44-82; SURVEY.md 8f "next-1") is
+  expressed with torch ops on the same device for now (inference semantics: dropouts off,
+  BatchNorm with moving statistics); it feeds the hot path and is not part of the measured
+  path.
+  """
+
+  def __init__(self, config, logger, class_n, device=None, seed=None, uhat_mode="fp32"):
+    self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    import math
+    self.stride = 2
+    self.cnn_n = config.model_conv_layer_num
+    self.feat_dim = math.ceil(config.feat_dim / (self.stride * self.cnn_n))   # naive:50
+    self.nfilt = config.model_conv_filter_num
+    self.class_n = class_n
+    self.enc_num = config.model_encoder_num
+    self.lpad, self.rpad = config.model_caps_window_lpad, config.model_caps_window_rpad
+    self.is_context = bool(config.model_caps_context)
+    self.iter = config.model_caps_iter
+    self.caps_inp_n, self.caps_inp_d = config.model_caps_primary_num, config.model_caps_primary_dim
+    self.stack = RoutingStack(
+        self.enc_num, config.model_caps_primary_num, config.model_caps_convolution_num, class_n,
+        config.model_caps_primary_dim, config.model_caps_convolution_dim, config.model_caps_class_dim,
+        self.lpad, self.rpad, self.iter, self.is_context,
+        inn_dropout=getattr(config, "train_inn_dropout", 0.1), device=self.device, seed=seed,
+        uhat_mode=uhat_mode)
+    self.fe = {}   # front-end parameters, TF layouts; filled by load_frontend / first call
+    self._fe_seed = seed
+    if logger is not None:
+      logger.info("Layer x %d, Iter x %d, Init %s, Win %d (l:%d, r:%d), "
+                  % (self.enc_num, self.iter, "SDR" if self.is_context else "DR",
+                     self.lpad + self.rpad + 1, self.lpad, self.rpad))
+
+  # -- parameters ------------------------------------------------------------------------
+  def _init_frontend(self, in_feat):
+    g = torch.Generator().manual_seed(0 if self._fe_seed is None else self._fe_seed)
+
+    def glorot(shape):
+      rf = 1
+      for s in shape[:-2]:
+        rf *= s
+      limit = (6.0 / (shape[-2] * rf + shape[-1] * rf)) ** 0.5
+      return ((torch.rand(shape, generator=g) * 2 - 1) * limit).to(self.device)
+
+    # the reference indexes conv_layers[0][conv_idx] / conv_layers[1][conv_idx]
+    # (sequence_router.py:76-77), so the SECOND index is the conv stage (SURVEY.md appendix D)
+    for li in range(2):
+      for pi in range(self.cnn_n):
+        cin = 1 if pi == 0 else self.nfilt
+        self.fe["cnn%d_%d_kernel" % (li, pi)] = glorot((3, 3, cin, self.nfilt))
+        self.fe["cnn%d_%d_bias" % (li, pi)] = torch.zeros(self.nfilt, device=self.device)
+    for li in range(self.cnn_n):
+      for n, v in (("gamma", 1.0), ("beta", 0.0), ("mean", 0.0), ("var", 1.0)):
+        self.fe["bn%d_%s" % (li, n)] = torch.full((self.nfilt,), v, device=self.device)
+    self.fe["dense_kernel"] = glorot((self.feat_dim * self.nfilt, self.caps_inp_n))
+    self.fe["dense_bias"] = torch.zeros(self.caps_inp_n, device=self.device)
+    for pi in range(2):
+      self.fe["encaps%d_kernel" % pi] = glorot((3, 3, 1, self.caps_inp_d))
+      self.fe["encaps%d_bias" % pi] = torch.zeros(self.caps_inp_d, device=self.device)
+    n = self.caps_inp_n * self.caps_inp_d
+    self.fe["ln_input_gamma"] = torch.ones(n, device=self.device)
+    self.fe["ln_input_beta"] = torch.zeros(n, device=self.device)
+
+  def load_frontend(self, params: dict):
+    """params: name -> array in the reference's (TF) layouts, names as in tests/golden."""
+    self.fe = {k: torch.as_tensor(v, dtype=torch.float32).to(self.device) for k, v in params.items()}
+
+  def named_parameters(self):
+    return [("frontend/" + k, v) for k, v in sorted(self.fe.items())] + self.stack.named_parameters()
+
+  def get_weights(self):
+    return [v.detach().cpu().numpy() for _, v in self.named_parameters()]
+
+  def set_weights(self, weights):
+    named = self.named_parameters()
+    if len(weights) != len(named):
+      raise ValueError("expected %d arrays, got %d" % (len(named), len(weights)))
+    for (name, t), w in zip(named, weights):
+      t.copy_(torch.as_tensor(w, dtype=torch.float32).reshape(t.shape))
+    self.stack.mark_weights_changed()
+
+  @property
+  def trainable_variables(self):
+    return [v for _, v in self.named_parameters()]
+
+  # -- forward ---------------------------------------------------------------------------
+  def capsulate(self, inputs, input_lengths):
+    """fbank [B,T,feat] -> primary capsules emb [B,S,PH,PD] (naive:129-142, inference)."""
+    x = routing_as_tensor(inputs, self.device)
+    lens = torch.as_tensor(input_lengths).to(self.device)
+    if not self.fe:
+      self._init_frontend(x.shape[-1])
+    f = self.fe
+    x = x[..., None]
+    for li in range(self.cnn_n):                       # sequence_router.py:71-81
+      x1 = _conv2d_same_nhwc(x, f["cnn0_%d_kernel" % li], f["cnn0_%d_bias" % li], self.stride)
+      x2 = _conv2d_same_nhwc(x, f["cnn1_%d_kernel" % li], f["cnn1_%d_bias" % li], self.stride)
+      x = torch.maximum(x1, x2)
+      x = _feat_mask(x, lens, self.stride ** (li + 1))
+      x = (x - f["bn%d_mean" % li]) / torch.sqrt(f["bn%d_var" % li] + 1e-3) * f["bn%d_gamma" % li] \
+          + f["bn%d_beta" % li]
+      x = _feat_mask(x, lens, self.stride ** (li + 1))
+    B, S = x.shape[0], x.shape[1]
+    emb = x.reshape(B, S, self.feat_dim * self.nfilt) @ f["dense_kernel"] + f["dense_bias"]
+    emb = emb[..., None]                               # [B,S,PH,1]
+    emb = torch.maximum(_conv2d_same_nhwc(emb, f["encaps0_kernel"], f["encaps0_bias"], 1),
+                        _conv2d_same_nhwc(emb, f["encaps1_kernel"], f["encaps1_bias"], 1))
+    emb = _feat_mask(emb, lens, self.stride ** 2)
+    n2 = (emb * emb).sum(-1, keepdim=True)             # squash, naive:248-253
+    emb = (n2 / (1.0 + n2)) * emb / torch.sqrt(n2 + 1e-7)
+    flat = emb.reshape(B, S, self.caps_inp_n * self.caps_inp_d)
+    flat = torch.nn.functional.layer_norm(flat, (flat.shape[-1],), f["ln_input_gamma"],
+                                          f["ln_input_beta"], eps=1e-3)
+    return flat.reshape(B, S, self.caps_inp_n, self.caps_inp_d).contiguous()
+
+  def __call__(self, inputs, input_lengths=None, training=False, **kwargs):
+    if input_lengths is None:
+      raise ValueError("input_lengths is required (naive:121)")
+    if training:
+      raise NotImplementedError(
+          "SequenceRouter front-end: training mode (dropout + BatchNorm batch statistics) is not "
+          "built yet; RoutingStack.forward(training=True) covers the routing path")
+    emb = self.capsulate(inputs, input_lengths)
+    return self.stack.forward(emb, training=False)
+
+  call = __call__
+
+
+def routing_as_tensor(x, device):
+  if not isinstance(x, torch.Tensor):
+    if hasattr(x, "__dlpack__"):
+      x = torch.from_dlpack(x)
+    else:
+      x = torch.as_tensor(x)
+  return x.to(device=device, dtype=torch.float32)

@@ -328,3 +328,35 @@ def test_streaming_kernel_is_deterministic_and_matches_register_variant(monkeypa
       outs[ns] = runs[0]
       h.close()
     assert rel_err(outs["0"], outs["1"].cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["sdr_i1_w3", "dr_i3_w7", "sdr_i2_w5"])
+def test_sequence_router_dropin_fbank_to_logits(name):
+  """The drop-in class end to end (fbank -> logits) against the vectors produced by the
+  reference's own source file: front-end (torch plumbing) + CUDA routing stack."""
+  import types
+  from srf_b200 import SequenceRouter
+  from tests import golden_util as gu
+  g = gu.load(name)
+  k, z = g["knobs"], g["raw"]
+  cfg = types.SimpleNamespace(
+      model_initializer="fan_avg", model_conv_layer_num=2, feat_dim=z["feats"].shape[-1],
+      model_conv_filter_num=z["fe_cnn0_0_kernel"].shape[-1], model_encoder_num=k["L"],
+      model_caps_iter=k["iters"], model_caps_window_lpad=k["lpad"], model_caps_window_rpad=k["rpad"],
+      model_caps_context=k["sdr"], model_caps_primary_num=k["PH"], model_caps_primary_dim=k["DIM"],
+      model_caps_convolution_num=k["CH"], model_caps_convolution_dim=k["DIM"],
+      model_caps_class_dim=k["DIM"], train_inp_dropout=0.1, train_inn_dropout=0.1)
+  model = SequenceRouter(cfg, None, k["class_n"])
+  model.load_frontend({n[3:]: z[n] for n in z.files if n.startswith("fe_")})
+  model.stack.load_oracle_params(g["params"])
+  emb = model.capsulate(torch.from_numpy(z["feats"]).float(), z["input_lengths"])
+  assert rel_err(emb, g["emb"]) < 1e-4
+  logits = model(torch.from_numpy(z["feats"]).float(), input_lengths=z["input_lengths"], training=False,
+                 mask=None, att_mask=None)
+  torch.cuda.synchronize()
+  assert rel_err(logits, g["logits"]) < 2e-4
+  lens = [int(n) // 4 for n in z["input_lengths"]]
+  assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(g["logits"], lens)
+  w = model.get_weights()
+  model.set_weights(w)
+  assert torch.equal(model(torch.from_numpy(z["feats"]).float(), input_lengths=z["input_lengths"]), logits)

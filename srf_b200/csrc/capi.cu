@@ -39,6 +39,7 @@ struct srf_handle {
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
   int force_F = 0, force_C = 0, no_stream = 0, max_stages = 0;
+  unsigned long long* dbg = nullptr;  // SRF_PHASE_TIMERS=1: per-CTA phase timers of the streaming kernel
   // tensor-core path
   std::vector<PackedWeights> packed_mma;
   void* ubuf = nullptr;  // materialised u_hat of one layer
@@ -134,6 +135,10 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_FORCE_C")) h->force_C = atoi(s);
   if (const char* s = getenv("SRF_NO_STREAM")) h->no_stream = atoi(s);
   if (const char* s = getenv("SRF_STREAM_STAGES")) h->max_stages = atoi(s);
+  if (const char* s = getenv("SRF_PHASE_TIMERS")) {
+    if (atoi(s) > 0 && cudaMalloc((void**)&h->dbg, 1024 * 8 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(h->dbg, 0, 1024 * 8 * sizeof(unsigned long long));
+  }
   *out = h;
   return 0;
 }
@@ -148,6 +153,7 @@ extern "C" int srf_destroy(srf_handle* h) {
     if (pw.Wp) cudaFree(pw.Wp);
   }
   if (h->ubuf) cudaFree(h->ubuf);
+  if (h->dbg) cudaFree(h->dbg);
   for (int i = 0; i < 2; ++i)
     if (h->ws[i]) cudaFree(h->ws[i]);
   delete h;
@@ -193,6 +199,17 @@ extern "C" int srf_profile_end(srf_handle* h, float* ms, int32_t* launches) {
   }
   h->spans.clear();
   return rc;
+}
+
+// debug aid (not part of the public header): copy the phase timers to the host and clear them
+extern "C" int srf_debug_phase_timers(srf_handle* h, unsigned long long* out, int n_cta) {
+  if (!h || !h->dbg) return -1;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  if (n_cta > 1024) n_cta = 1024;
+  cudaMemcpy(out, h->dbg, (size_t)n_cta * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(h->dbg, 0, 1024 * 8 * sizeof(unsigned long long));
+  return 0;
 }
 
 extern "C" int64_t srf_launch_count(const srf_handle* h) { return h ? h->launches : 0; }
@@ -569,6 +586,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
   p.halfB = halfB;
 
   p.nstage = 0;
+  p.dbg = h->dbg;
   // (fp32 u_hat storage stays on the in-kernel register-prefetch variant)
   if (um == 1 && !h->no_stream) {
     // streaming kernel: TMA-fed ring + warp-specialised output; needs >= 2 ring stages

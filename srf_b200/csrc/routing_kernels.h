@@ -30,6 +30,7 @@ struct RouteParams {
   const void* u;  // materialised u_hat (streaming modes), else null
   int halfB;      // frame pairs per time step = ceil(B/2)
   int nstage;     // streaming kernel: depth of the shared-memory u_hat ring
+  unsigned long long* dbg;  // optional phase timers [CTA][8] (clock64 sums), null = off
 };
 
 // u_hat GEMM (uhat_gemm.cu)

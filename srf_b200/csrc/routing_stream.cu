@@ -83,6 +83,38 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 enum { BAR_COMPUTE = 1 };
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // remote store of 4 floats into a peer CTA's shared memory that completes (by byte count) on
 // that peer's mbarrier: data visibility and signalling in one instruction, no fences.
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
@@ -137,8 +169,8 @@ route_stream_kernel(const RouteParams p) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], NCW);
     }
-    ptx::mbar_init(&xfull[0], 1);
-    ptx::mbar_init(&xfull[1], 1);
+    ptx::mbar_init(&xfull[0], 1 + NCW);  // expect_tx arrive + one arrive per consumer warp
+    ptx::mbar_init(&xfull[1], 1 + NCW);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&vready[b], 2 / FPW);  // one arrive per slot-0 consumer warp
       ptx::mbar_init(&vfree[b], 2);  // one arrive per output warp
@@ -177,7 +209,10 @@ route_stream_kernel(const RouteParams p) {
     // ============================== consumers ==============================
     const int slot = FPW == 1 ? (warp >> 1) : warp;   // capsule slot inside a stage
     const int f0 = FPW == 1 ? (warp & 1) : 0;         // first pair member of this warp
-    const uint32_t ushift = f0 ? 0u : 16u;            // bf16 member select: (w << ushift) & 0xffff0000
+    // bf16 -> fp32 of pair member f0 in one PRMT: bytes (0, 0, lo, hi) of the selected half
+    const uint32_t usel = f0 ? 0x3244u : 0x1044u;
+    const uint32_t ring_a = ptx::smem_u32(ring) + (uint32_t)slot * SLAB + (uint32_t)lane * (BF16 ? 16u : 32u);
+    const uint32_t full_a = ptx::smem_u32(full), empty_a = ptx::smem_u32(empty);
     int st = 0;
     uint32_t ph = 0;
     uint32_t npass = 0;   // exchange counter
@@ -200,20 +235,23 @@ route_stream_kernel(const RouteParams p) {
           for (int q = 0; q < OPL; ++q)
 #pragma unroll
             for (int k = 0; k < T; ++k) ta[f][q][k] = 0.f;
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
+        const bool timing = p.dbg != nullptr && tid == 0;
+        if (timing) tk0 = clock64();
 
         for (int base = i_lo; base < i_hi; base += NSLOT) {
           const int i = base + slot;
           uint4 raw[RAWN];
-          ptx::mbar_wait(&full[st], ph);
+          while (!mbar_try_wait_a(full_a + st * 8, ph)) {
+          }
           if (i < i_hi) {
-            const uint4* slab =
-                reinterpret_cast<const uint4*>(ring + (size_t)st * STAGE + (size_t)slot * SLAB);
+            const uint32_t a0 = ring_a + (uint32_t)st * STAGE;
 #pragma unroll
             for (int m = 0; m < RAWN; ++m)
-              raw[m] = BF16 ? slab[m * 32 + lane] : slab[(m >> 1) * 64 + lane * 2 + (m & 1)];
+              raw[m] = BF16 ? lds128(a0 + m * 512) : lds128(a0 + (m >> 1) * 1024 + (m & 1) * 16);
           }
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&empty[st]);
+          if (lane == 0) mbar_arrive_a(empty_a + st * 8);
           if (++st == NSTAGE) {
             st = 0;
             ph ^= 1;
@@ -234,8 +272,7 @@ route_stream_kernel(const RouteParams p) {
                     u[0][q][k4 * 4 + kin] = __uint_as_float(w[kin] << 16);
                     u[FPW - 1][q][k4 * 4 + kin] = __uint_as_float(w[kin] & 0xffff0000u);
                   } else {
-                    // member 0 = low half (<< 16), member 1 = high half (mask): one LOP3/SHF each
-                    u[0][q][k4 * 4 + kin] = __uint_as_float((w[kin] << ushift) & 0xffff0000u);
+                    u[0][q][k4 * 4 + kin] = __uint_as_float(__byte_perm(w[kin], 0u, usel));
                   }
                 }
               } else {
@@ -291,11 +328,11 @@ route_stream_kernel(const RouteParams p) {
             float z = 0.f;
 #pragma unroll
             for (int q = 0; q < OPL; ++q) {
-              ex[q] = exp2f((a[f][q] - m) * LOG2E);
+              ex[q] = fast_ex2((a[f][q] - m) * LOG2E);
               z += ex[q];
             }
             z = wsum(z);
-            const float inv = 1.0f / z;
+            const float inv = fast_rcp(z);
 #pragma unroll
             for (int q = 0; q < OPL; ++q) {
               const float c = ex[q] * inv;
@@ -305,6 +342,7 @@ route_stream_kernel(const RouteParams p) {
           }
         }
 
+        if (timing) tk1 = clock64();
         // ---- reduce t over the capsule slots of this CTA -------------------------------------
 #pragma unroll
         for (int f = 0; f < FPW; ++f)
@@ -314,8 +352,9 @@ route_stream_kernel(const RouteParams p) {
             for (int k = 0; k < T; ++k)
               red[slot * E + (f0 + f) * EF + (q * T + k) * 32 + lane] = ta[f][q][k];
         const int par = npass & 1;
-        if (C > 1 && tid == 0) ptx::mbar_arrive_expect_tx(&xfull[par], (uint32_t)C * E * 4);
+        if (C > 1 && tid == 0) ptx::mbar_arrive_expect_tx(&xfull[par], (uint32_t)(C - 1) * E * 4);
         named_sync(BAR_COMPUTE, NCT);
+        if (timing) tk2 = clock64();
         {
           // sum the NSLOT warp partials (float4 = 4 consecutive lanes) and publish the CTA partial:
           // locally for C == 1, else into every peer's xbuf[par][rank] with st.async
@@ -332,20 +371,28 @@ route_stream_kernel(const RouteParams p) {
               acc.z += x.z;
               acc.w += x.w;
             }
+            reinterpret_cast<float4*>(mine)[e4] = acc;  // own copy: plain shared store
             if (C > 1) {
-              for (int r = 0; r < C; ++r)
-                st_async_v4(map_to_rank(mine_a + e4 * 16, r), acc, map_to_rank(bar_a, r));
-            } else {
-              reinterpret_cast<float4*>(mine)[e4] = acc;
+              for (int r = 1; r < C; ++r) {
+                const int peer = (rank + r) & (C - 1);  // C is a power of two
+                st_async_v4(map_to_rank(mine_a + e4 * 16, peer), acc, map_to_rank(bar_a, peer));
+              }
             }
           }
+          if (C > 1) {
+            // the local stores are published to the CTA by one mbarrier arrive per warp
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&xfull[par]);
+          }
         }
+        if (timing) tk3 = clock64();
         if (C > 1) {
           ptx::mbar_wait(&xfull[par], (npass >> 1) & 1);
         } else {
           named_sync(BAR_COMPUTE, NCT);
         }
         ++npass;
+        if (timing) tk4 = clock64();
 
         // ---- cluster sum (cooperative, float4) -> tot[0..E) ------------------------------------
         if (C > 1) {
@@ -364,6 +411,7 @@ route_stream_kernel(const RouteParams p) {
           named_sync(BAR_COMPUTE, NCT);
         }
         const float* total = C > 1 ? tot : xbuf + (size_t)par * E;
+        if (timing) tk5 = clock64();
         // ---- squash (naive:248-253) + Vacc update: every consumer warp does this for its own
         // (member, lane) columns, the result feeds its registers directly; the slot-0 warps also
         // hand v to the output warps.
@@ -381,7 +429,8 @@ route_stream_kernel(const RouteParams p) {
               t[k] = xb[k * 32];
               n2 = fmaf(t[k], t[k], n2);
             }
-            const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
+            // n2/(1+n2) / sqrt(n2+eps) with approximate rsqrt / rcp (tensor-path tolerance class)
+            const float scale = n2 * rsqrtf(n2 + 1e-7f) * fast_rcp(1.0f + n2);
             float* vo = vout + (size_t)(s & 1) * E + (size_t)(f0 + f) * EF + q * T * 32 + lane;
 #pragma unroll
             for (int k = 0; k < T; ++k) {
@@ -397,6 +446,17 @@ route_stream_kernel(const RouteParams p) {
         if (writer) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&vready[s & 1]);
+        }
+        if (timing) {
+          const long long tk6 = clock64();
+          unsigned long long* d = p.dbg + (size_t)blockIdx.x * 8;
+          d[0] += (unsigned long long)(tk1 - tk0);  // capsule loop
+          d[1] += (unsigned long long)(tk2 - tk1);  // store partials + CTA barrier
+          d[2] += (unsigned long long)(tk3 - tk2);  // local sum + push
+          d[3] += (unsigned long long)(tk4 - tk3);  // wait for the peers' partials
+          d[4] += (unsigned long long)(tk5 - tk4);  // cluster sum + barrier
+          d[5] += (unsigned long long)(tk6 - tk5);  // squash + hand-off
+          d[6] += 1;
         }
       }
     }

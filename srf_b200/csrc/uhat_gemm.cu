@@ -59,7 +59,11 @@ __global__ void pack_weights_mma_kernel(const float* __restrict__ W, const float
       const int j = jb * 32 + r / 4, k = k4 * 4 + (r & 3), l = c * 4 + li;
       float v = 0.f;
       if (j < O && k < D && l < d) v = W[(((long long)i * O + j) * D + k) * d + l];
-      Wm[e] = v;
+      // the tensor core truncates fp32 operands to TF32; round to nearest here instead so the
+      // weight operand carries no truncation bias
+      uint32_t tf;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tf) : "f"(v));
+      Wm[e] = __uint_as_float(tf);
     } else {
       long long q = e - nW;
       const int r = (int)(q % 128);

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRF_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define SRF_B200_VERSION 101 /* major*10000 + minor*100 + patch */
 
 typedef struct srf_handle srf_handle;
 
@@ -53,6 +53,8 @@ enum {
  *   out_caps     [B,S,O,D]     layer output (after LN and dropout); may be NULL in a
  *                              stack call (library workspace is used)
  *   out_logits   [B,S,O]       required iff head_gamma != NULL
+ *   out_raw      [B,S,O,D]     optional: the squashed capsules BEFORE LayerNorm/dropout
+ *                              (what the backward pass needs saved); NULL = not written
  */
 typedef struct srf_layer_desc {
   const float* emb;
@@ -65,6 +67,7 @@ typedef struct srf_layer_desc {
   const float* head_beta;
   float* out_caps;
   float* out_logits;
+  float* out_raw;
   int32_t B, S;        /* utterances, routing frames per utterance                    */
   int32_t H, d;        /* input capsules per frame, input capsule dim                 */
   int32_t O, D;        /* output capsules, output capsule dim                         */
@@ -101,6 +104,37 @@ int srf_route_layer_fwd(srf_handle* h, const srf_layer_desc* layer, void* stream
  * The B,S of all layers must agree and layers[n].H,d must equal layers[n-1].O,D.
  */
 int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, int32_t n_layers,
+                        void* stream);
+
+/*
+ * Backward of one routing layer (training mode of naive:145-193; the reference gets it from
+ * tf.GradientTape through the tf.while_loop, tfsr/trainer_sr.py:62-71).  `layer` is the SAME
+ * descriptor the forward call used (emb, W, bias, LayerNorm/head parameters, dropout mask,
+ * knobs; its out_* pointers are ignored).  All gradient outputs ACCUMULATE (+=): zero them
+ * before the first call.  u_hat is recomputed in FP32 inside the kernel (nothing but the
+ * layer input and `v_raw` is saved by the forward pass).
+ *   v_raw        [B,S,O,D]  forward's out_raw of this layer
+ *   d_out        [B,S,O,D]  dL/d(out_caps) from the next layer's d_emb; NULL on the last layer
+ *   d_logits     [B,S,O]    dL/d(out_logits); NULL unless the layer carries the head
+ *   d_raw        [B,S,O,D]  scratch: dL/d(v_raw) is left here
+ *   dW [I,O,D,d], dbias [I,O,D], dgamma/dbeta [O*D] (NULL if no LayerNorm),
+ *   dhead_gamma/dhead_beta [O] (NULL if no head), d_emb [B,S,H,d] (NULL = not needed)
+ */
+typedef struct srf_layer_grads {
+  const float* v_raw;
+  const float* d_out;
+  const float* d_logits;
+  float* d_raw;
+  float* dW;
+  float* dbias;
+  float* dgamma;
+  float* dbeta;
+  float* dhead_gamma;
+  float* dhead_beta;
+  float* d_emb;
+} srf_layer_grads;
+
+int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* layer, const srf_layer_grads* grads,
                         void* stream);
 
 /*

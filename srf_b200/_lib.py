@@ -14,7 +14,7 @@ UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF1
 
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",
-           "srf_route_stack_fwd", "srf_uhat_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
+           "srf_route_stack_fwd", "srf_route_layer_bwd", "srf_uhat_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
            "srf_last_kernel")
 
 
@@ -24,12 +24,18 @@ class LayerDesc(Structure):
       ("emb", c_void_p), ("W", c_void_p), ("bias", c_void_p),
       ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("dropout_mask", c_void_p),
       ("head_gamma", c_void_p), ("head_beta", c_void_p),
-      ("out_caps", c_void_p), ("out_logits", c_void_p),
+      ("out_caps", c_void_p), ("out_logits", c_void_p), ("out_raw", c_void_p),
       ("B", c_int32), ("S", c_int32), ("H", c_int32), ("d", c_int32),
       ("O", c_int32), ("D", c_int32), ("lpad", c_int32), ("rpad", c_int32),
       ("iters", c_int32), ("sdr", c_int32), ("mask_class0", c_int32), ("uhat_mode", c_int32),
       ("ln_eps", c_float), ("length_eps", c_float), ("weights_version", c_uint64),
   ]
+
+
+class LayerGrads(Structure):
+  """struct srf_layer_grads (include/srf_b200.h)."""
+  _fields_ = [(n, c_void_p) for n in ("v_raw", "d_out", "d_logits", "d_raw", "dW", "dbias", "dgamma",
+                                      "dbeta", "dhead_gamma", "dhead_beta", "d_emb")]
 
 
 _lib = None
@@ -55,6 +61,8 @@ def load() -> ctypes.CDLL:
   lib.srf_route_layer_fwd.restype = c_int
   lib.srf_route_stack_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_int32, c_void_p]
   lib.srf_route_stack_fwd.restype = c_int
+  lib.srf_route_layer_bwd.argtypes = [c_void_p, POINTER(LayerDesc), POINTER(LayerGrads), c_void_p]
+  lib.srf_route_layer_bwd.restype = c_int
   lib.srf_uhat_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_void_p, c_void_p]
   lib.srf_uhat_fwd.restype = c_int
   lib.srf_profile_begin.argtypes = [c_void_p]

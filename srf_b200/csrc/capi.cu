@@ -218,7 +218,7 @@ extern "C" const char* srf_last_kernel(const srf_handle* h) {
   return h ? h->last_kernel.c_str() : "";
 }
 
-static int validate_layer(srf_handle* h, const srf_layer_desc* L) {
+static int validate_layer(srf_handle* h, const srf_layer_desc* L, bool fwd = true) {
   if (!L) return fail(h, -1, "layer descriptor is NULL");
   if (!L->emb || !L->W || !L->bias) return fail(h, -1, "emb, W and bias must be non-NULL");
   if (L->B < 0 || L->S < 0) return fail(h, -2, "negative B or S");
@@ -232,7 +232,8 @@ static int validate_layer(srf_handle* h, const srf_layer_desc* L) {
     return fail(h, -1, "ln_gamma and ln_beta must both be given or both be NULL");
   if ((L->head_gamma == nullptr) != (L->head_beta == nullptr))
     return fail(h, -1, "head_gamma and head_beta must both be given or both be NULL");
-  if (L->head_gamma && !L->out_logits) return fail(h, -1, "head requested but out_logits is NULL");
+  if (fwd && L->head_gamma && !L->out_logits)
+    return fail(h, -1, "head requested but out_logits is NULL");
   if (L->uhat_mode != SRF_UHAT_FP32 && L->uhat_mode != SRF_UHAT_TF32 &&
       L->uhat_mode != SRF_UHAT_BF16)
     return fail(h, -4, "unknown uhat_mode %d", L->uhat_mode);
@@ -496,7 +497,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
   if (L && (L->B == 0 || L->S == 0)) return 0;  // empty batch: nothing to do
   int rc = validate_layer(h, L);
   if (rc) return rc;
-  if (!L->out_caps && !L->out_logits) return fail(h, -1, "no output requested");
+  if (!L->out_caps && !L->out_logits && !L->out_raw) return fail(h, -1, "no output requested");
 
   const int window = L->lpad + L->rpad + 1;
   const int I = window * L->H;
@@ -565,6 +566,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
   p.head_beta = L->head_beta;
   p.out_caps = L->out_caps;
   p.out_logits = L->out_logits;
+  p.out_raw = L->out_raw;
   p.B = L->B;
   p.S = L->S;
   p.H = L->H;
@@ -637,6 +639,86 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
            "%sroute_layer_kernel<T=%d,OPL=%d,F=%d,NW=%d,UM=%d> C=%d groups=%d smem=%zu",
            um != 0 ? "uhat_gemm_kernel(tcgen05 tf32) + " : "", T, OPL, F, SRF_NW, um, C, groups, smem);
   h->last_kernel = name;
+  return 0;
+}
+
+extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const srf_layer_grads* G,
+                                   void* stream_) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (!L || !G) return fail(h, -1, "layer descriptor or grads is NULL");
+  if (L->B == 0 || L->S == 0) return 0;
+  DeviceGuard guard(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = validate_layer(h, L, false);
+  if (rc) return rc;
+  if (!G->v_raw || !G->d_raw || !G->dW || !G->dbias)
+    return fail(h, -1, "v_raw, d_raw, dW and dbias must be non-NULL");
+  if (!G->d_out && !G->d_logits) return fail(h, -1, "neither d_out nor d_logits given");
+  if (G->d_logits && (!L->head_gamma || !G->dhead_gamma || !G->dhead_beta))
+    return fail(h, -1, "d_logits needs head_gamma and dhead_gamma/dhead_beta");
+  if (L->ln_gamma && (!G->dgamma || !G->dbeta)) return fail(h, -1, "LayerNorm needs dgamma/dbeta");
+  if (L->iters > 8) return fail(h, -3, "backward supports iters <= 8");
+  const int window = L->lpad + L->rpad + 1;
+  const int I = window * L->H;
+  const int m = L->D > L->d ? L->D : L->d;
+  const int T = m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 20 ? 20 : 32));
+  const int OPL = L->O <= 32 ? 1 : (L->O <= 64 ? 2 : 4);
+  if ((T >= 16 && OPL > 2) || (T == 32 && OPL > 1))
+    return fail(h, -3, "backward: O=%d with D=%d is not instantiated", L->O, L->D);
+  const PackedWeights* pw = nullptr;
+  rc = get_packed(h, L, I, T, 32 * OPL, stream, &pw);
+  if (rc) return rc;
+  srf::BwdParams p;
+  p.emb = L->emb;
+  p.Wp = pw->Wp;
+  p.Bp = pw->Bp;
+  p.ln_gamma = L->ln_gamma;
+  p.ln_beta = L->ln_beta;
+  p.dropout_mask = L->dropout_mask;
+  p.head_gamma = L->head_gamma;
+  p.v_raw = G->v_raw;
+  p.d_out = G->d_out;
+  p.d_logits = G->d_logits;
+  p.d_raw = G->d_raw;
+  p.dW = G->dW;
+  p.dbias = G->dbias;
+  p.dgamma = G->dgamma;
+  p.dbeta = G->dbeta;
+  p.dhead_gamma = G->dhead_gamma;
+  p.dhead_beta = G->dhead_beta;
+  p.d_emb = G->d_emb;
+  p.B = L->B;
+  p.S = L->S;
+  p.H = L->H;
+  p.d = L->d;
+  p.O = L->O;
+  p.D = L->D;
+  p.I = I;
+  p.lpad = L->lpad;
+  p.iters = L->iters;
+  p.sdr = L->sdr ? 1 : 0;
+  p.mask0 = L->mask_class0 ? 1 : 0;
+  p.nsteps = L->sdr ? L->S : 1;
+  p.ln_eps = L->ln_eps;
+  p.length_eps = L->length_eps;
+  {
+    KernelSpan span(h, 2, stream);
+    srf::launch_ln_head_bwd(p, stream);
+  }
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, "ln_head_bwd launch");
+  const long long nchains = L->sdr ? L->B : (long long)L->B * L->S;
+  {
+    KernelSpan span(h, 2, stream);
+    e = srf::launch_route_layer_bwd(p, T, OPL, (int)nchains, stream);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return cuda_fail(h, e, "route_layer_bwd launch");
+  }
+  h->launches++;
+  h->last_kernel = "ln_head_bwd_kernel + route_layer_bwd_kernel";
   return 0;
 }
 

@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_kernel(const RouteParams 
           if (j < O) {
             for (int k = 0; k < D; ++k) {
               float y = vf[(q * T + k) * 32 + lane];
+              if (p.out_raw && frame_ok) p.out_raw[(frame * O + j) * D + k] = y;
               if (do_ln) y = (y - mean) * rstd * __ldg(p.ln_gamma + j * D + k) + __ldg(p.ln_beta + j * D + k);
               if (p.dropout_mask && frame_ok) y *= __ldg(p.dropout_mask + (frame * O + j) * D + k);
               if (p.out_caps && frame_ok) p.out_caps[(frame * O + j) * D + k] = y;

@@ -20,6 +20,7 @@ struct RouteParams {
   const float* head_beta;
   float* out_caps;            // [B,S,O,D] or null
   float* out_logits;          // [B,S,O] or null
+  float* out_raw;             // [B,S,O,D] pre-LayerNorm capsules or null
   int B, S, H, d, O, D, I;
   int lpad, iters, sdr, mask0;
   int C;        // cluster size (CTAs that split the input capsules of one chain group)
@@ -32,6 +33,34 @@ struct RouteParams {
   int nstage;     // streaming kernel: depth of the shared-memory u_hat ring
   unsigned long long* dbg;  // optional phase timers [CTA][8] (clock64 sums), null = off
 };
+
+// backward (routing_bwd.cu)
+struct BwdParams {
+  const float* emb;
+  const float* Wp;
+  const float* Bp;
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* dropout_mask;
+  const float* head_gamma;
+  const float* v_raw;
+  const float* d_out;
+  const float* d_logits;
+  float* d_raw;
+  float* dW;
+  float* dbias;
+  float* dgamma;
+  float* dbeta;
+  float* dhead_gamma;
+  float* dhead_beta;
+  float* d_emb;
+  int B, S, H, d, O, D, I;
+  int lpad, iters, sdr, mask0, nsteps;
+  float ln_eps, length_eps;
+};
+void launch_ln_head_bwd(const BwdParams& p, cudaStream_t stream);
+cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int nchains,
+                                   cudaStream_t stream);
 
 // u_hat GEMM (uhat_gemm.cu)
 struct UhatParams {

@@ -502,6 +502,13 @@ route_stream_kernel(const RouteParams p) {
         frame = (long long)bb * p.S + ss;
       }
       if (!ok) continue;
+      if (p.out_raw) {
+#pragma unroll
+        for (int q = 0; q < OPL; ++q)
+#pragma unroll
+          for (int k = 0; k < T; ++k)
+            if (q * 32 + lane < O && k < D) p.out_raw[(frame * O + q * 32 + lane) * D + k] = y[q][k];
+      }
       if (do_ln) {
         float sum = 0.f;
 #pragma unroll

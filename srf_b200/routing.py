@@ -230,3 +230,57 @@ def uhat_fwd(emb, W, bias, lpad: int, rpad: int, uhat_mode: str = "tf32",
   rc = h.lib.srf_uhat_fwd(h._h, ctypes.byref(desc), ctypes.c_void_p(out.data_ptr()), stream)
   _lib.check(h.lib, h._h, rc, "srf_uhat_fwd")
   return out
+
+
+def route_layer_fwd_train(emb, args: LayerArgs, handle: Optional[Handle] = None):
+  """Forward of one layer that also returns the pre-LayerNorm capsules the backward needs:
+  -> (capsules [B,S,O,D], logits or None, v_raw [B,S,O,D])."""
+  emb = as_device_tensor(emb)
+  h = handle or default_handle(emb.device)
+  _prep(args, emb.device)
+  B, S, H, d = emb.shape
+  O, D = args.W.shape[1], args.W.shape[2]
+  out_caps = torch.empty((B, S, O, D), dtype=torch.float32, device=emb.device)
+  out_raw = torch.empty((B, S, O, D), dtype=torch.float32, device=emb.device)
+  out_logits = torch.empty((B, S, O), dtype=torch.float32, device=emb.device) \
+      if args.head_gamma is not None else None
+  desc = _lib.LayerDesc()
+  _fill_desc(desc, args, emb, B, S, H, d, out_caps, out_logits)
+  desc.out_raw = _ptr(out_raw)
+  stream = ctypes.c_void_p(torch.cuda.current_stream(emb.device).cuda_stream)
+  rc = h.lib.srf_route_layer_fwd(h._h, ctypes.byref(desc), stream)
+  _lib.check(h.lib, h._h, rc, "srf_route_layer_fwd")
+  return out_caps, out_logits, out_raw
+
+
+def route_layer_bwd(emb, args: LayerArgs, v_raw, d_out=None, d_logits=None, need_d_emb=True,
+                    handle: Optional[Handle] = None):
+  """Backward of one layer (srf_route_layer_bwd).  Returns a dict with dW, dbias, dgamma, dbeta,
+  dhead_gamma, dhead_beta (None where the layer has no such parameter) and d_emb."""
+  emb = as_device_tensor(emb)
+  h = handle or default_handle(emb.device)
+  _prep(args, emb.device)
+  dev = emb.device
+  B, S, H, d = emb.shape
+  I, O, D, _ = args.W.shape
+  z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+  g = {"dW": z(I, O, D, d), "dbias": z(I, O, D),
+       "dgamma": z(O * D) if args.ln_gamma is not None else None,
+       "dbeta": z(O * D) if args.ln_gamma is not None else None,
+       "dhead_gamma": z(O) if d_logits is not None else None,
+       "dhead_beta": z(O) if d_logits is not None else None,
+       "d_emb": z(B, S, H, d) if need_d_emb else None}
+  d_raw = torch.empty((B, S, O, D), dtype=torch.float32, device=dev)
+  v_raw = as_device_tensor(v_raw, dev)
+  d_out = None if d_out is None else as_device_tensor(d_out, dev)
+  d_logits = None if d_logits is None else as_device_tensor(d_logits, dev)
+  desc = _lib.LayerDesc()
+  _fill_desc(desc, args, emb, B, S, H, d, None, None)
+  gr = _lib.LayerGrads()
+  gr.v_raw, gr.d_out, gr.d_logits, gr.d_raw = _ptr(v_raw), _ptr(d_out), _ptr(d_logits), _ptr(d_raw)
+  gr.dW, gr.dbias, gr.dgamma, gr.dbeta = _ptr(g["dW"]), _ptr(g["dbias"]), _ptr(g["dgamma"]), _ptr(g["dbeta"])
+  gr.dhead_gamma, gr.dhead_beta, gr.d_emb = _ptr(g["dhead_gamma"]), _ptr(g["dhead_beta"]), _ptr(g["d_emb"])
+  stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  rc = h.lib.srf_route_layer_bwd(h._h, ctypes.byref(desc), ctypes.byref(gr), stream)
+  _lib.check(h.lib, h._h, rc, "srf_route_layer_bwd")
+  return g

@@ -127,6 +127,51 @@ class RoutingStack:
 
   __call__ = forward
 
+  # -- training step pieces (BASELINE.json cfg-4) ------------------------------------------
+  def forward_train(self, emb, dropout_masks=None):
+    """Forward that keeps what the backward needs (layer inputs, pre-LayerNorm capsules,
+    dropout masks).  Returns logits [B,S,class_n]."""
+    emb = routing.as_device_tensor(emb, self.device)
+    if dropout_masks is None and self.inn_dropout > 0:
+      dropout_masks = self.make_dropout_masks(emb.shape[0], emb.shape[1])
+    args = self.layer_args(dropout_masks)
+    self._saved = []
+    x, logits = emb, None
+    for a in args:
+      caps, lg, raw = routing.route_layer_fwd_train(x, a, self.handle)
+      self._saved.append((x, a, raw))
+      x, logits = caps, lg
+    return logits
+
+  def backward(self, d_logits, need_d_emb=True):
+    """Backward through the routing stack of the last forward_train.  Returns
+    ({parameter name: gradient}, d_emb)."""
+    grads, d_out, n = {}, None, len(self._saved)
+    for i in reversed(range(n)):
+      x, a, raw = self._saved[i]
+      g = routing.route_layer_bwd(x, a, raw, d_out=d_out, d_logits=d_logits if i == n - 1 else None,
+                                  need_d_emb=need_d_emb or i > 0, handle=self.handle)
+      grads["W%d" % i], grads["b%d" % i] = g["dW"], g["dbias"]
+      grads["ln_mid%d/gamma" % (i + 1)], grads["ln_mid%d/beta" % (i + 1)] = g["dgamma"], g["dbeta"]
+      if i == n - 1:
+        grads["ln_output/gamma"], grads["ln_output/beta"] = g["dhead_gamma"], g["dhead_beta"]
+      d_out = g["d_emb"]
+    self._saved = []
+    return grads, d_out
+
+  def ctc_train_step_grads(self, emb, labels, input_lengths, label_lengths, dropout_masks=None):
+    """fwd + CTC loss + bwd (tfsr/trainer_sr.py:56-71).  The CTC loss itself (tf.nn.ctc_loss in
+    the reference, blank = class_n - 1, SURVEY.md 8f "next-2") is taken from torch here; the
+    routing forward/backward run in the CUDA library.  Returns (loss, grads, d_emb)."""
+    logits = self.forward_train(emb, dropout_masks)
+    lt = logits.detach().requires_grad_(True)
+    logp = torch.log_softmax(lt, dim=-1).transpose(0, 1)
+    loss = torch.nn.functional.ctc_loss(logp, labels, input_lengths, label_lengths,
+                                        blank=self.class_n - 1, reduction="sum", zero_infinity=True)
+    loss.backward()
+    grads, d_emb = self.backward(lt.grad)
+    return loss.detach(), grads, d_emb
+
 
 # ----------------------------------------------------------------------------------------
 # Drop-in model class

@@ -26,7 +26,7 @@ def test_python_binding_lists_every_symbol(built_lib):
   from srf_b200 import _lib
   assert sorted(_lib.EXPORTS) == _declared_symbols()
   lib = _lib.load()
-  assert lib.srf_version() == 100
+  assert lib.srf_version() == 101
 
 
 def test_layer_desc_matches_header_layout():
@@ -47,8 +47,8 @@ def test_layer_desc_matches_header_layout():
     for extra in decl.split(",")[1:]:
       fields.append(extra.replace("*", " ").strip())
   assert fields == [n for n, _ in _lib.LayerDesc._fields_]
-  # 10 pointers + 12 int32 + 2 float + 1 uint64
-  assert ctypes.sizeof(_lib.LayerDesc) == 10 * 8 + 12 * 4 + 2 * 4 + 8
+  # 11 pointers + 12 int32 + 2 float + 1 uint64
+  assert ctypes.sizeof(_lib.LayerDesc) == 11 * 8 + 12 * 4 + 2 * 4 + 8
 
 
 def test_no_gpu_means_loud_failure(built_lib):

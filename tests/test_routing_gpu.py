@@ -409,3 +409,95 @@ def test_full_size_cfg3_properties():
   assert rel_err(e_sl[:, :safe], ref[:, :safe]) < 1e-4
   lens = [safe, safe]
   assert o.greedy_ctc(e_sl[:, :safe].cpu(), lens) == o.greedy_ctc(ref[:, :safe], lens)
+
+
+# ----------------------------------------------------------------------------------------
+# backward (cfg-4): gradients against torch autograd of the oracle (float64)
+# ----------------------------------------------------------------------------------------
+BWD_CASES = [
+    # B, S, H, d, O, D, lpad, rpad, iters, sdr, last
+    (2, 5, 6, 8, 5, 8, 1, 1, 1, True, False),
+    (2, 4, 6, 8, 7, 8, 1, 1, 1, True, True),
+    (2, 4, 5, 8, 6, 8, 1, 0, 3, True, False),
+    (2, 4, 5, 8, 6, 8, 0, 1, 2, False, True),
+    (3, 3, 7, 4, 9, 12, 1, 1, 2, True, True),     # d != D
+    (2, 3, 12, 20, 30, 20, 1, 1, 1, True, False),  # WSJ dims
+    (1, 4, 6, 8, 40, 8, 0, 0, 2, False, True),     # 2 output capsules per lane
+]
+
+
+@pytest.mark.parametrize("case", BWD_CASES)
+def test_layer_backward_matches_autograd(case):
+  from srf_b200 import routing
+  B, S, H, d, O, D, lpad, rpad, iters, sdr, last = case
+  g = torch.Generator().manual_seed(31)
+  win = lpad + rpad + 1
+  emb = torch.randn(B, S, H, d, generator=g, dtype=torch.float64)
+  W = (torch.randn(win * H, O, D, d, generator=g, dtype=torch.float64) * 0.3)
+  bias = (torch.randn(win * H, O, D, generator=g, dtype=torch.float64) * 0.3)
+  gam = 1 + 0.2 * torch.randn(O * D, generator=g, dtype=torch.float64)
+  bet = 0.1 * torch.randn(O * D, generator=g, dtype=torch.float64)
+  hg = 1 + 0.2 * torch.randn(O, generator=g, dtype=torch.float64)
+  hb = 0.1 * torch.randn(O, generator=g, dtype=torch.float64)
+  mask = ((torch.rand(B, S, O, D, generator=g) < 0.9).double() / 0.9)
+  wl = torch.randn(B, S, O, generator=g, dtype=torch.float64)      # loss weights
+  wc = torch.randn(B, S, O, D, generator=g, dtype=torch.float64)
+  leaves = [t.requires_grad_(True) for t in (emb, W, bias, gam, bet, hg, hb)]
+  v = o.route_layer(emb, W, bias, lpad, rpad, iters, sdr, last)
+  y = o.layer_norm(v.reshape(B, S, O * D), gam, bet).reshape(B, S, O, D) * mask
+  if last:
+    logits = o.layer_norm(o.length(y), hg, hb)
+    loss = (logits * wl).sum()
+  else:
+    loss = (y * wc).sum()
+  loss.backward()
+  f = lambda t: t.detach().float().cuda()
+  args = routing.LayerArgs(W=f(W), bias=f(bias), lpad=lpad, rpad=rpad, iters=iters, sdr=sdr,
+                           mask_class0=last, ln_gamma=f(gam), ln_beta=f(bet), dropout_mask=f(mask),
+                           head_gamma=f(hg) if last else None, head_beta=f(hb) if last else None)
+  caps, lg, raw = routing.route_layer_fwd_train(f(emb), args)
+  assert rel_err(raw, v.detach()) < 1e-4
+  got = routing.route_layer_bwd(f(emb), args, raw, d_out=None if last else f(wc),
+                                d_logits=f(wl) if last else None)
+  torch.cuda.synchronize()
+  checks = [("dW", W.grad), ("dbias", bias.grad), ("dgamma", gam.grad), ("dbeta", bet.grad), ("d_emb", emb.grad)]
+  if last:
+    checks += [("dhead_gamma", hg.grad), ("dhead_beta", hb.grad)]
+  for name, ref in checks:
+    assert rel_err(got[name].reshape(ref.shape), ref) < 2e-4, name
+
+
+def test_stack_ctc_train_step_grads_match_autograd():
+  """fwd + CTC loss + bwd through a 3-layer SDR stack vs autograd of the oracle."""
+  from srf_b200 import RoutingStack
+  L, PH, CH, class_n, DIM, lpad, rpad, iters, B, S = 3, 10, 6, 9, 8, 1, 1, 1, 3, 12
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1)
+  p32 = o.init_params(shapes, class_n, seed=4, random_ln=True)
+  p = p32.to(torch.float64)
+  emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+  labels = torch.tensor([[1, 3, 2, 0], [4, 4, 5, 1], [2, 6, 0, 0]])
+  in_len, lab_len = torch.tensor([12, 10, 9]), torch.tensor([3, 4, 2])
+  g = torch.Generator().manual_seed(8)
+  masks = [((torch.rand(B, S, s[1], s[2], generator=g) < 0.9).double() / 0.9) for s in shapes]
+  leaves = p.W + p.bias + p.ln_gamma + p.ln_beta + [p.lno_gamma, p.lno_beta, emb]
+  for t in leaves:
+    t.requires_grad_(True)
+  logits = o.route_stack(emb, p, lpad, rpad, iters, True, dropout_masks=masks)
+  loss = torch.nn.functional.ctc_loss(torch.log_softmax(logits, -1).transpose(0, 1), labels, in_len, lab_len,
+                                      blank=class_n - 1, reduction="sum", zero_infinity=True)
+  loss.backward()
+  stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, True, seed=0)
+  stack.load_oracle_params(p32)
+  got_loss, grads, d_emb = stack.ctc_train_step_grads(
+      emb.detach().float().cuda(), labels.cuda(), in_len.cuda(), lab_len.cuda(),
+      dropout_masks=[m.float().cuda() for m in masks])
+  torch.cuda.synchronize()
+  assert abs(got_loss.item() - loss.item()) / abs(loss.item()) < 1e-4
+  for i in range(L):
+    assert rel_err(grads["W%d" % i], p.W[i].grad) < 5e-4, i
+    assert rel_err(grads["b%d" % i], p.bias[i].grad) < 5e-4, i
+    assert rel_err(grads["ln_mid%d/gamma" % (i + 1)], p.ln_gamma[i].grad) < 5e-4, i
+    assert rel_err(grads["ln_mid%d/beta" % (i + 1)], p.ln_beta[i].grad) < 5e-4, i
+  assert rel_err(grads["ln_output/gamma"], p.lno_gamma.grad) < 5e-4
+  assert rel_err(grads["ln_output/beta"], p.lno_beta.grad) < 5e-4
+  assert rel_err(d_emb, emb.grad) < 5e-4

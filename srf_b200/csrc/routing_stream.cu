@@ -269,46 +269,50 @@ route_stream_kernel(const RouteParams p) {
             }
           // agreement with the accumulated outputs (naive:205 / :223 / :240)
           float a[FPW][OPL];
-          bool small = true;
 #pragma unroll
           for (int q = 0; q < OPL; ++q) {
             const int jp = q * 32 + lane;
             const bool valid = (jp < O) && !(p.mask0 && jp == 0);
 #pragma unroll
             for (int f = 0; f < FPW; ++f) {
-              float acc0 = 0.f, acc1 = 0.f;
+              float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
-              for (int k = 0; k < T; k += 2) {
+              for (int k = 0; k < T; k += 4) {
                 acc0 = fmaf(u[f][q][k], va[f][q][k], acc0);
                 acc1 = fmaf(u[f][q][k + 1], va[f][q][k + 1], acc1);
+                acc2 = fmaf(u[f][q][k + 2], va[f][q][k + 2], acc2);
+                acc3 = fmaf(u[f][q][k + 3], va[f][q][k + 3], acc3);
               }
-              const float acc = acc0 + acc1;
-              small = small && (fabsf(acc) < 60.f);
-              a[f][q] = valid ? acc : -CUDART_INF_F;
+              a[f][q] = valid ? (acc0 + acc1) + (acc2 + acc3) : -CUDART_INF_F;
             }
           }
           // coupling softmax over output capsules (naive:202 / :225 / :241) + weighted sum.
-          // softmax is shift invariant: when every logit of the warp is small the max
-          // subtraction (a 5-step shuffle chain) is skipped; otherwise the usual stable form.
-          const bool fast = __all_sync(0xffffffffu, small);
+          // Both warp reductions are single REDUX instructions: the max on an order-preserving
+          // integer image of the floats, the sum on a Q26 fixed-point image of exp(a - max) in
+          // (0, 1] (32 terms <= 2^31, unsigned; the normaliser keeps ~2^-21 relative accuracy, the
+          // coefficients themselves stay fp32).
 #pragma unroll
           for (int f = 0; f < FPW; ++f) {
-            float m = 0.f;
-            if (!fast) {
-              m = a[f][0];
+            float m = a[f][0];
 #pragma unroll
-              for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[f][q]);
-              m = wmax(m);
-            }
+            for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[f][q]);
+            int mi = __float_as_int(m);
+            mi ^= (mi >> 31) & 0x7fffffff;
+            mi = __reduce_max_sync(0xffffffffu, mi);
+            mi ^= (mi >> 31) & 0x7fffffff;
+            m = __int_as_float(mi);
             float ex[OPL];
-            float z = 0.f;
+            float zl = 0.f;
 #pragma unroll
             for (int q = 0; q < OPL; ++q) {
               ex[q] = fast_ex2((a[f][q] - m) * LOG2E);
-              z += ex[q];
+              zl += ex[q];
             }
-            z = wsum(z);
-            const float inv = fast_rcp(z);
+            // OPL <= 4 terms per lane, each <= 1: Q(26 - log2 OPL) keeps the warp sum below 2^31
+            constexpr float QS = (float)(1 << 26) / (float)OPL;
+            // unsigned: 32 lanes x 2^26 = 2^31 exactly when the coupling is uniform
+            const unsigned zi = __reduce_add_sync(0xffffffffu, __float2uint_rn(zl * QS));
+            const float inv = fast_rcp((float)zi * (1.0f / QS));
 #pragma unroll
             for (int q = 0; q < OPL; ++q) {
               const float c = ex[q] * inv;

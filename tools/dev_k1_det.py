@@ -5,7 +5,7 @@ from oracle import srf_oracle as o
 def mk(B,S,H,d,O,D,win,seed):
     g=torch.Generator().manual_seed(seed)
     return torch.randn(B,S,H,d,generator=g), torch.randn(win*H,O,D,d,generator=g)*0.1, torch.randn(win*H,O,D,generator=g)*0.1
-for (B,S,H,d,O,D,lpad,rpad) in ((4,8,60,8,30,8,1,1),(2,3,20,8,30,8,0,0),(64,7,60,20,30,20,2,2)):
+for (B,S,H,d,O,D,lpad,rpad) in ((2,6,30,8,63,8,1,1),(2,6,30,8,30,8,1,1),(4,6,30,8,63,8,1,1)):
   emb,W,bias=mk(B,S,H,d,O,D,lpad+rpad+1,17)
   ref=o.prediction_vectors(o.window_gather(emb.double(),lpad,rpad),W.double(),bias.double())
   for mode in ('tf32','bf16'):

@@ -16,7 +16,7 @@ for case in cases:
         os.environ['SRF_STREAM_STAGES']=st
         os.environ['SRF_NO_STREAM']='0'
         h=routing.Handle()
-        a=routing.LayerArgs(W=W.cuda(),bias=bias.cuda(),lpad=lpad,rpad=rpad,iters=iters,sdr=sdr,mask_class0=(iters==3),uhat_mode='bf16')
+        a=routing.LayerArgs(W=W.cuda(),bias=bias.cuda(),lpad=lpad,rpad=rpad,iters=iters,sdr=sdr,mask_class0=(iters==3),uhat_mode=os.environ.get('SOAK_MODE','bf16'))
         outs=[routing.route_layer_fwd(emb.cuda(),a,handle=h)[0].clone() for _ in range(10)]
         torch.cuda.synchronize()
         os.environ['SRF_NO_STREAM']='1'

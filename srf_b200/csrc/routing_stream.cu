@@ -490,23 +490,19 @@ route_stream_kernel(const RouteParams p) {
             if (q * 32 + lane < O && k < D) p.out_raw[(frame * O + q * 32 + lane) * D + k] = y[q][k];
       }
       if (do_ln) {
-        float sum = 0.f;
+        // padded capsules / dims hold exact zeros (zero weights -> t = 0 -> v = 0), so the sums
+        // need no predicates; variance in one pass: E[y^2] - mean^2
+        float sum = 0.f, sq = 0.f;
 #pragma unroll
         for (int q = 0; q < OPL; ++q)
 #pragma unroll
-          for (int k = 0; k < T; ++k)
-            if (q * 32 + lane < O && k < D) sum += y[q][k];
+          for (int k = 0; k < T; ++k) {
+            sum += y[q][k];
+            sq = fmaf(y[q][k], y[q][k], sq);
+          }
         const float mean = wsum(sum) * inv_n;
-        float sq = 0.f;
-#pragma unroll
-        for (int q = 0; q < OPL; ++q)
-#pragma unroll
-          for (int k = 0; k < T; ++k)
-            if (q * 32 + lane < O && k < D) {
-              const float dv = y[q][k] - mean;
-              sq = fmaf(dv, dv, sq);
-            }
-        const float rstd = 1.0f / sqrtf(wsum(sq) * inv_n + p.ln_eps);
+        const float var = fmaxf(wsum(sq) * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.ln_eps);
 #pragma unroll
         for (int q = 0; q < OPL; ++q)
 #pragma unroll

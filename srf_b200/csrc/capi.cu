@@ -38,7 +38,7 @@ struct srf_handle {
   std::vector<PackedWeights> packed;
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
-  int force_F = 0, force_C = 0, no_stream = 0, max_stages = 0, stream_fp32 = 0;
+  int force_F = 0, force_C = 0, no_stream = 0, max_stages = 0;
   unsigned long long* dbg = nullptr;  // SRF_PHASE_TIMERS=1: per-CTA phase timers of the streaming kernel
   // tensor-core path
   std::vector<PackedWeights> packed_mma;
@@ -135,7 +135,6 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_FORCE_C")) h->force_C = atoi(s);
   if (const char* s = getenv("SRF_NO_STREAM")) h->no_stream = atoi(s);
   if (const char* s = getenv("SRF_STREAM_STAGES")) h->max_stages = atoi(s);
-  if (const char* s = getenv("SRF_STREAM_FP32")) h->stream_fp32 = atoi(s);
   if (const char* s = getenv("SRF_PHASE_TIMERS")) {
     if (atoi(s) > 0 && cudaMalloc((void**)&h->dbg, 1024 * 8 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(h->dbg, 0, 1024 * 8 * sizeof(unsigned long long));
@@ -590,8 +589,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
 
   p.nstage = 0;
   p.dbg = h->dbg;
-  // (fp32 u_hat storage stays on the in-kernel register-prefetch variant)
-  if ((um == 1 || h->stream_fp32) && !h->no_stream) {
+  if (um != 0 && !h->no_stream) {
     // streaming kernel: TMA-fed ring + warp-specialised output; needs >= 2 ring stages
     int Cs = C;
     if (Cs * groups > h->num_sms) Cs = pow2_floor(h->num_sms / groups > 0 ? h->num_sms / groups : 1);

@@ -215,6 +215,7 @@ route_stream_kernel(const RouteParams p) {
         const bool timing = p.dbg != nullptr && tid == 0;
         if (timing) tk0 = clock64();
 
+        int rel_st = -1;  // stage still to be released
         for (int base = i_lo; base < i_hi; base += NSLOT) {
           const int i = base + slot;
           uint4 raw[RAWN];
@@ -226,8 +227,14 @@ route_stream_kernel(const RouteParams p) {
             for (int m = 0; m < RAWN; ++m)
               raw[m] = BF16 ? lds128(a0 + m * 512) : lds128(a0 + (m >> 1) * 1024 + (m & 1) * 16);
           }
+          // The stage is handed back to the producer one round LATE (at the top of the next
+          // round, or after the loop): by then every register loaded from it has been consumed
+          // by a full round of math, so no shared-memory load of this warp can still be in
+          // flight when the TMA engine overwrites the stage.  (Arriving right after issuing the
+          // loads let the refill race with loads delayed by bank-conflict replays.)
           __syncwarp();
-          if (lane == 0) mbar_arrive_a(empty_a + st * 8);
+          if (lane == 0 && rel_st >= 0) mbar_arrive_a(empty_a + rel_st * 8);
+          rel_st = st;
           if (++st == NSTAGE) {
             st = 0;
             ph ^= 1;
@@ -331,6 +338,9 @@ route_stream_kernel(const RouteParams p) {
 #pragma unroll
             for (int k = 0; k < T; ++k)
               red[slot * E + (f0 + f) * EF + (q * T + k) * 32 + lane] = ta[f][q][k];
+        // release the last stage of the pass (its data went into the ta just stored)
+        __syncwarp();
+        if (lane == 0 && rel_st >= 0) mbar_arrive_a(empty_a + rel_st * 8);
         const int par = npass & 1;
         if (C > 1 && tid == 0) ptx::mbar_arrive_expect_tx(&xfull[par], (uint32_t)(C - 1) * E * 4);
         named_sync(BAR_COMPUTE, NCT);

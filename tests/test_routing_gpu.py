@@ -306,9 +306,12 @@ def test_tensor_path_full_stack(case, mode):
   assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(ref_logits, lens)
 
 
-def test_streaming_kernel_is_deterministic_and_matches_register_variant(monkeypatch):
-  """The TMA-fed streaming routing kernel (bf16 u_hat) against the in-kernel prefetch variant on
-  the same materialised u_hat, and against itself over repeated launches."""
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_streaming_kernel_is_deterministic_and_matches_register_variant(monkeypatch, mode):
+  """The TMA-fed streaming routing kernel against the in-kernel prefetch variant on the same
+  materialised u_hat, and against itself over repeated launches (regression test for the ring
+  write-after-read hazard: a stage must not be handed back to the TMA producer while loads from
+  it can still be in flight)."""
   from srf_b200 import routing
   for case, sdr, iters in (((4, 8, 60, 8, 30, 8, 1, 1), True, 1), ((5, 7, 30, 20, 32, 20, 2, 2), True, 2),
                            ((8, 9, 30, 8, 30, 8, 3, 3), False, 3), ((2, 6, 30, 8, 63, 8, 1, 1), True, 3)):
@@ -319,8 +322,8 @@ def test_streaming_kernel_is_deterministic_and_matches_register_variant(monkeypa
       monkeypatch.setenv("SRF_NO_STREAM", ns)
       h = routing.Handle()
       a = routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=lpad, rpad=rpad, iters=iters, sdr=sdr,
-                            mask_class0=False, uhat_mode="bf16")
-      runs = [routing.route_layer_fwd(emb.cuda(), a, handle=h)[0].clone() for _ in range(5)]
+                            mask_class0=False, uhat_mode=mode)
+      runs = [routing.route_layer_fwd(emb.cuda(), a, handle=h)[0].clone() for _ in range(8)]
       torch.cuda.synchronize()
       assert ("route_stream_kernel" in h.last_kernel) == (ns == "0")
       for r in runs[1:]:

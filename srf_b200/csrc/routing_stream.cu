@@ -115,6 +115,14 @@ route_stream_kernel(const RouteParams p) {
   constexpr int NCT = NCW * 32;                // consumer threads
   constexpr int EF = OPL * T * 32;             // t tile of ONE pair member: (q*T+k)*32+lane
   constexpr int E = 2 * EF;                    // both members: f*EF + ...
+  // FPW == 1: the warps of pair member 0 and of pair member 1 form two independent TEAMS (the
+  // members are different utterances): own named barrier, own exchange buffers and mbarriers.
+  // The teams share only the u_hat ring, so they drift out of phase and one team's
+  // reduce/exchange/squash tail overlaps the other team's capsule loop.
+  constexpr int NTEAM = FPW == 1 ? 2 : 1;
+  constexpr int TW = NCW / NTEAM;              // warps per team
+  constexpr int TT = TW * 32;                  // threads per team
+  constexpr int ET = E / NTEAM;                // t elements a team owns
   constexpr int SLAB = OPL * T4 * 128 * 2 * (BF16 ? 2 : 4);  // bytes of u_hat per (pair, capsule)
   constexpr int STAGE = NSLOT * SLAB;
   constexpr int RAWN = SLAB / 512;             // uint4 per lane per capsule
@@ -136,20 +144,19 @@ route_stream_kernel(const RouteParams p) {
   float* vout = tot + E;                                           // [2][E]
   uint64_t* full = reinterpret_cast<uint64_t*>(vout + 2 * E);      // [NSTAGE]
   uint64_t* empty = full + NSTAGE;                                 // [NSTAGE]
-  uint64_t* xfull = empty + NSTAGE;                                // [2]
-  uint64_t* vready = xfull + 2;                                    // [2] v of frame s is in vout[s&1]
-  uint64_t* vfree = vready + 2;                                    // [2] output warps are done with it
+  uint64_t* xfull = empty + NSTAGE;                                // [team][2]
+  uint64_t* vready = xfull + 4;                                    // [member][2] v of frame s is in vout[s&1]
+  uint64_t* vfree = vready + 4;                                    // [member][2] the output warp is done with it
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], NCW);
     }
-    ptx::mbar_init(&xfull[0], 1 + NCW);  // expect_tx arrive + one arrive per consumer warp
-    ptx::mbar_init(&xfull[1], 1 + NCW);
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&vready[b], 2 / FPW);  // one arrive per slot-0 consumer warp
-      ptx::mbar_init(&vfree[b], 2);  // one arrive per output warp
+    for (int b = 0; b < 4; ++b) {
+      ptx::mbar_init(&xfull[b], 1 + TW);  // expect_tx arrive + one arrive per warp of the team
+      ptx::mbar_init(&vready[b], 1);
+      ptx::mbar_init(&vfree[b], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -185,6 +192,10 @@ route_stream_kernel(const RouteParams p) {
     // ============================== consumers ==============================
     const int slot = FPW == 1 ? (warp >> 1) : warp;   // capsule slot inside a stage
     const int f0 = FPW == 1 ? (warp & 1) : 0;         // first pair member of this warp
+    const int team = f0;                              // (0 when FPW == 2)
+    const int ttid = FPW == 1 ? slot * 32 + lane : tid;   // thread index inside the team
+    const int tb = team * ET;                         // the team's offset inside E-sized buffers
+    const int bar_id = BAR_COMPUTE + team;
     // bf16 -> fp32 of pair member f0 in one PRMT: bytes (0, 0, lo, hi) of the selected half
     const uint32_t usel = f0 ? 0x3244u : 0x1044u;
     const uint32_t ring_a = ptx::smem_u32(ring) + (uint32_t)slot * SLAB + (uint32_t)lane * (BF16 ? 16u : 32u);
@@ -342,20 +353,22 @@ route_stream_kernel(const RouteParams p) {
         __syncwarp();
         if (lane == 0 && rel_st >= 0) mbar_arrive_a(empty_a + rel_st * 8);
         const int par = npass & 1;
-        if (C > 1 && tid == 0) ptx::mbar_arrive_expect_tx(&xfull[par], (uint32_t)(C - 1) * E * 4);
-        named_sync(BAR_COMPUTE, NCT);
+        uint64_t* xf = &xfull[team * 2 + par];
+        if (C > 1 && ttid == 0) ptx::mbar_arrive_expect_tx(xf, (uint32_t)(C - 1) * ET * 4);
+        named_sync(bar_id, TT);
         if (timing) tk2 = clock64();
         {
           // sum the NSLOT warp partials (float4 = 4 consecutive lanes) and publish the CTA partial:
-          // locally for C == 1, else into every peer's xbuf[par][rank] with st.async
-          float* mine = xbuf + ((size_t)par * C + rank) * E;
+          // own copy with a plain store, the peers' copies with st.async into their xbuf[par][rank]
+          float* mine = xbuf + ((size_t)par * C + rank) * E + tb;
           const uint32_t mine_a = ptx::smem_u32(mine);
-          const uint32_t bar_a = ptx::smem_u32(&xfull[par]);
-          for (int e4 = tid; e4 < E / 4; e4 += NCT) {
-            float4 acc = reinterpret_cast<const float4*>(red)[e4];
+          const uint32_t bar_a = ptx::smem_u32(xf);
+          const float4* red4 = reinterpret_cast<const float4*>(red + tb);
+          for (int e4 = ttid; e4 < ET / 4; e4 += TT) {
+            float4 acc = red4[e4];
 #pragma unroll
             for (int w = 1; w < NSLOT; ++w) {
-              const float4 x = reinterpret_cast<const float4*>(red + w * E)[e4];
+              const float4 x = red4[(size_t)w * (E / 4) + e4];
               acc.x += x.x;
               acc.y += x.y;
               acc.z += x.z;
@@ -370,24 +383,24 @@ route_stream_kernel(const RouteParams p) {
             }
           }
           if (C > 1) {
-            // the local stores are published to the CTA by one mbarrier arrive per warp
+            // the local stores are published to the team by one mbarrier arrive per warp
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&xfull[par]);
+            if (lane == 0) ptx::mbar_arrive(xf);
           }
         }
         if (timing) tk3 = clock64();
         if (C > 1) {
-          ptx::mbar_wait(&xfull[par], (npass >> 1) & 1);
+          ptx::mbar_wait(xf, (npass >> 1) & 1);
         } else {
-          named_sync(BAR_COMPUTE, NCT);
+          named_sync(bar_id, TT);
         }
         ++npass;
         if (timing) tk4 = clock64();
 
-        // ---- cluster sum (cooperative, float4) -> tot[0..E) ------------------------------------
+        // ---- cluster sum (cooperative, float4) -> tot ------------------------------------------
         if (C > 1) {
-          const float4* xb4 = reinterpret_cast<const float4*>(xbuf + (size_t)par * C * E);
-          for (int e4 = tid; e4 < E / 4; e4 += NCT) {
+          const float4* xb4 = reinterpret_cast<const float4*>(xbuf + (size_t)par * C * E + tb);
+          for (int e4 = ttid; e4 < ET / 4; e4 += TT) {
             float4 acc = xb4[e4];
             for (int r = 1; r < C; ++r) {
               const float4 x = xb4[(size_t)r * (E / 4) + e4];
@@ -396,9 +409,9 @@ route_stream_kernel(const RouteParams p) {
               acc.z += x.z;
               acc.w += x.w;
             }
-            reinterpret_cast<float4*>(tot)[e4] = acc;
+            reinterpret_cast<float4*>(tot + tb)[e4] = acc;
           }
-          named_sync(BAR_COMPUTE, NCT);
+          named_sync(bar_id, TT);
         }
         const float* total = C > 1 ? tot : xbuf + (size_t)par * E;
         if (timing) tk5 = clock64();
@@ -406,7 +419,10 @@ route_stream_kernel(const RouteParams p) {
         // (member, lane) columns, the result feeds its registers directly; the slot-0 warps also
         // hand v to the output warps.
         const bool writer = last_pass && slot == 0;
-        if (writer && s >= 2) ptx::mbar_wait(&vfree[s & 1], ((s >> 1) - 1) & 1);
+        if (writer && s >= 2) {
+#pragma unroll
+          for (int f = 0; f < FPW; ++f) ptx::mbar_wait(&vfree[(f0 + f) * 2 + (s & 1)], ((s >> 1) - 1) & 1);
+        }
 #pragma unroll
         for (int f = 0; f < FPW; ++f)
 #pragma unroll
@@ -435,7 +451,10 @@ route_stream_kernel(const RouteParams p) {
           }
         if (writer) {
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&vready[s & 1]);
+          if (lane == 0) {
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) ptx::mbar_arrive(&vready[(f0 + f) * 2 + (s & 1)]);
+          }
         }
         if (timing) {
           const long long tk6 = clock64();
@@ -470,7 +489,7 @@ route_stream_kernel(const RouteParams p) {
     }
     const float inv_n = 1.0f / (float)(O * D);
     for (int s = 0; s < p.nsteps; ++s) {
-      ptx::mbar_wait(&vready[s & 1], (s >> 1) & 1);
+      ptx::mbar_wait(&vready[f * 2 + (s & 1)], (s >> 1) & 1);
       const float* vf = vout + (size_t)(s & 1) * E + (size_t)f * EF;
       float y[OPL][T];
 #pragma unroll
@@ -478,7 +497,7 @@ route_stream_kernel(const RouteParams p) {
 #pragma unroll
         for (int k = 0; k < T; ++k) y[q][k] = vf[(q * T + k) * 32 + lane];
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&vfree[s & 1]);
+      if (lane == 0) ptx::mbar_arrive(&vfree[f * 2 + (s & 1)]);
 
       long long frame;
       bool ok;
@@ -590,7 +609,7 @@ static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_
 size_t route_stream_fixed_smem(int T, int OPL, int C, int max_stages) {
   const size_t E = (size_t)2 * OPL * T * 32;
   return sizeof(float) * ((size_t)SRF_NW * E + (size_t)2 * C * E + 3 * E) +
-         sizeof(uint64_t) * (2 * (size_t)max_stages + 6) + 128;
+         sizeof(uint64_t) * (2 * (size_t)max_stages + 12) + 128;
 }
 size_t route_stream_stage_bytes(int T, int OPL, bool bf16) {
   return (size_t)SRF_NW * OPL * (T / 4) * 128 * 2 * (bf16 ? 2 : 4);

@@ -165,6 +165,7 @@ def main():
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other configs")
   ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "bf16"],
                   help="u_hat arithmetic: bf16 = tcgen05 TF32 MMA + bf16 u_hat storage (default), "
                        "tf32 = same with fp32 storage, fp32 = exact FP32 CUDA-core kernel")
@@ -328,6 +329,26 @@ def main():
       "clocks": clocks,
       "roofline": roofline,
   }
+  if world == 1 and not args.no_also:
+    # the other single-GPU configurations of BASELINE.json, same build, short runs (not the
+    # headline: parity-test cases that are cheap enough to time beside it)
+    line["also"] = {}
+    for name in sorted(WORKLOADS):
+      if name == args.workload:
+        continue
+      ww = WORKLOADS[name]
+      Bw, Sw = ww["B"], (ww["T"] + 3) // 4
+      st2 = RoutingStack(ww["L"], ww["PH"], ww["CH"], ww["class_n"], ww["DIM"], ww["DIM"], ww["DIM"],
+                         ww["lpad"], ww["rpad"], ww["iters"], ww["sdr"], device=dev, seed=0,
+                         uhat_mode=args.uhat)
+      e2 = torch.randn(Bw, Sw, ww["PH"], ww["DIM"], device=dev)
+      o2 = torch.empty(Bw, Sw, ww["class_n"], device=dev)
+      for _ in range(3):
+        st2.forward(e2, out_logits=o2)
+      ms2 = timed(lambda i: st2.forward(e2, out_logits=o2), 20) / 20
+      line["also"][name] = {"workload": ww["desc"], "ms_per_step": ms2,
+                            "value": Bw * Sw / (ms2 / 1e3), "unit": "routing frames/s",
+                            "note": "inputs resident; working set fits L2"}
   if rank == 0 and not args.no_cpu_baseline and world == 1:
     n_utts, n_frames = cpu_sample_shape(w, big=True)
     fps, dt = cpu_reference_run(w, n_utts, n_frames, repeats=2)

@@ -138,6 +138,38 @@ int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* layer, const srf_la
                         void* stream);
 
 /*
+ * Greedy CTC decode (the parity criterion of SURVEY.md 8c; blank = class_n - 1,
+ * tfsr/trainer_sr.py:133-134): argmax per routing frame for s < lens[b], collapse repeats, drop
+ * blank.  logits [B,S,C]; lens [B] int32 (routing frames); out_ids [B,S] int32 (first out_lens[b]
+ * entries valid); out_lens [B] int32.
+ */
+int srf_ctc_greedy_decode(srf_handle* h, const float* logits, const int32_t* lens, int32_t B,
+                          int32_t S, int32_t C, int32_t blank, int32_t* out_ids, int32_t* out_lens,
+                          void* stream);
+
+/*
+ * CTC loss and its gradient (tf.nn.ctc_loss(labels, logits, label_length, logit_length,
+ * logits_time_major=False, blank_index=blank), tfsr/trainer_sr.py:64-66).  logits [B,S,C] are
+ * unnormalised (log-softmax is applied inside, as TF does); labels [B,Lmax] int32; in_lens,
+ * lab_lens [B] int32.  loss [B] receives the per-utterance negative log-likelihood; d_logits
+ * [B,S,C] receives grad_scale * dloss/dlogits (grad_scale = 1/global_batch reproduces
+ * tf.nn.compute_average_loss, trainer_sr.py:67-68).  Utterances with no feasible alignment get
+ * loss 0 and a zero gradient.
+ */
+int srf_ctc_loss(srf_handle* h, const float* logits, const int32_t* labels, const int32_t* in_lens,
+                 const int32_t* lab_lens, int32_t B, int32_t S, int32_t C, int32_t Lmax, int32_t blank,
+                 float grad_scale, float* loss, float* d_logits, void* stream);
+
+/*
+ * One Adam update on a flat fp32 buffer with tf.keras.optimizers.Adam semantics
+ * (tfsr/helper/train_helper.py:58-68; beta1 .9, beta2 .98, eps 1e-9 in egs/conf): step >= 1 is the
+ * 1-based update count, lr the already scheduled learning rate (warm-up schedule
+ * train_helper.py:32-56, see srf_b200.training.warmup_lr).
+ */
+int srf_adam_step(srf_handle* h, float* param, const float* grad, float* m, float* v, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/*
  * prediction vectors alone: window gather + u_hat = W.x + bias (naive:150-159) for every frame,
  * written in the reference's [B,S,I,O,D] layout (naive:158), fp32.  Uses emb, W, bias, B,S,H,d,
  * O,D, lpad, rpad and uhat_mode of the descriptor: SRF_UHAT_TF32 / SRF_UHAT_BF16 run the tcgen05

@@ -5,7 +5,7 @@ Public surface:
     RoutingStack     -- the routing stack alone (primary capsules -> CTC logits)
     routing          -- tensor-level wrappers of the C-ABI (include/srf_b200.h)
 """
-from . import _lib, routing  # noqa: F401
+from . import _lib, routing, training  # noqa: F401
 from .sequence_router import RoutingStack, SequenceRouter, layer_shapes  # noqa: F401
 
 __all__ = ["routing", "RoutingStack", "SequenceRouter", "layer_shapes"]

@@ -14,7 +14,8 @@ UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF1
 
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",
-           "srf_route_stack_fwd", "srf_route_layer_bwd", "srf_uhat_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
+           "srf_route_stack_fwd", "srf_route_layer_bwd", "srf_ctc_greedy_decode", "srf_ctc_loss",
+           "srf_adam_step", "srf_uhat_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
            "srf_last_kernel")
 
 
@@ -63,6 +64,15 @@ def load() -> ctypes.CDLL:
   lib.srf_route_stack_fwd.restype = c_int
   lib.srf_route_layer_bwd.argtypes = [c_void_p, POINTER(LayerDesc), POINTER(LayerGrads), c_void_p]
   lib.srf_route_layer_bwd.restype = c_int
+  lib.srf_ctc_greedy_decode.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_void_p, c_void_p]
+  lib.srf_ctc_greedy_decode.restype = c_int
+  lib.srf_ctc_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                               c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]
+  lib.srf_ctc_loss.restype = c_int
+  lib.srf_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                c_float, c_float, c_int64, c_void_p]
+  lib.srf_adam_step.restype = c_int
   lib.srf_uhat_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_void_p, c_void_p]
   lib.srf_uhat_fwd.restype = c_int
   lib.srf_profile_begin.argtypes = [c_void_p]

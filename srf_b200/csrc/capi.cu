@@ -39,6 +39,8 @@ struct srf_handle {
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
   int force_F = 0, force_C = 0, no_stream = 0, max_stages = 0;
+  float* ctc_ws = nullptr;  // alpha workspace of srf_ctc_loss
+  size_t ctc_ws_bytes = 0;
   unsigned long long* dbg = nullptr;  // SRF_PHASE_TIMERS=1: per-CTA phase timers of the streaming kernel
   // tensor-core path
   std::vector<PackedWeights> packed_mma;
@@ -154,6 +156,7 @@ extern "C" int srf_destroy(srf_handle* h) {
   }
   if (h->ubuf) cudaFree(h->ubuf);
   if (h->dbg) cudaFree(h->dbg);
+  if (h->ctc_ws) cudaFree(h->ctc_ws);
   for (int i = 0; i < 2; ++i)
     if (h->ws[i]) cudaFree(h->ws[i]);
   delete h;
@@ -162,6 +165,63 @@ extern "C" int srf_destroy(srf_handle* h) {
 
 extern "C" const char* srf_last_error(const srf_handle* h) {
   return h ? h->error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int srf_ctc_greedy_decode(srf_handle* h, const float* logits, const int32_t* lens, int32_t B,
+                                     int32_t S, int32_t C, int32_t blank, int32_t* out_ids,
+                                     int32_t* out_lens, void* stream) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (B == 0) return 0;
+  if (!logits || !lens || !out_ids || !out_lens) return fail(h, -1, "NULL argument");
+  if (B < 0 || S <= 0 || C <= 0 || blank < 0 || blank >= C) return fail(h, -2, "bad shape or blank index");
+  DeviceGuard g(h->device);
+  srf::launch_ctc_greedy(logits, lens, B, S, C, blank, out_ids, out_lens, (cudaStream_t)stream);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, "ctc_greedy launch");
+  return 0;
+}
+
+extern "C" int srf_ctc_loss(srf_handle* h, const float* logits, const int32_t* labels,
+                            const int32_t* in_lens, const int32_t* lab_lens, int32_t B, int32_t S,
+                            int32_t C, int32_t Lmax, int32_t blank, float grad_scale, float* loss,
+                            float* d_logits, void* stream_) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (B == 0) return 0;
+  if (!logits || !labels || !in_lens || !lab_lens || !loss || !d_logits) return fail(h, -1, "NULL argument");
+  if (B < 0 || S <= 0 || C <= 1 || Lmax <= 0 || blank < 0 || blank >= C)
+    return fail(h, -2, "bad shape or blank index");
+  DeviceGuard g(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t need = (size_t)B * S * (2 * (size_t)Lmax + 1) * sizeof(float);
+  if (need > h->ctc_ws_bytes) {
+    if (h->ctc_ws) cudaFreeAsync(h->ctc_ws, stream);
+    h->ctc_ws = nullptr;
+    h->ctc_ws_bytes = 0;
+    cudaError_t e = cudaMallocAsync((void**)&h->ctc_ws, need, stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "CTC workspace allocation");
+    h->ctc_ws_bytes = need;
+  }
+  cudaError_t e = srf::launch_ctc_loss(logits, labels, in_lens, lab_lens, B, S, C, Lmax, blank, grad_scale,
+                                       loss, d_logits, h->ctc_ws, stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "ctc_loss launch");
+  h->launches++;
+  return 0;
+}
+
+extern "C" int srf_adam_step(srf_handle* h, float* param, const float* grad, float* m, float* v,
+                             int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                             void* stream) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (n == 0) return 0;
+  if (!param || !grad || !m || !v) return fail(h, -1, "NULL argument");
+  if (n < 0 || step < 1) return fail(h, -2, "n must be >= 0 and step >= 1");
+  DeviceGuard g(h->device);
+  srf::launch_adam(param, grad, m, v, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, "adam launch");
+  return 0;
 }
 
 extern "C" int srf_profile_begin(srf_handle* h) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 #ifndef SRF_NW
 #define SRF_NW 8  // warps per CTA of the fused FP32 layer kernel
@@ -61,6 +62,16 @@ struct BwdParams {
 void launch_ln_head_bwd(const BwdParams& p, cudaStream_t stream);
 cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int nchains,
                                    cudaStream_t stream);
+
+// CTC + Adam (ctc_adam.cu)
+void launch_ctc_greedy(const float* logits, const int32_t* lens, int B, int S, int C, int blank,
+                       int32_t* out_ids, int32_t* out_lens, cudaStream_t stream);
+cudaError_t launch_ctc_loss(const float* logits, const int32_t* labels, const int32_t* in_lens,
+                            const int32_t* lab_lens, int B, int S, int C, int Lmax, int blank,
+                            float scale, float* loss, float* d_logits, float* alpha_ws,
+                            cudaStream_t stream);
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                 float beta2, float eps, long long step, cudaStream_t stream);
 
 // u_hat GEMM (uhat_gemm.cu)
 struct UhatParams {

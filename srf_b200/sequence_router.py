@@ -160,17 +160,14 @@ class RoutingStack:
     return grads, d_out
 
   def ctc_train_step_grads(self, emb, labels, input_lengths, label_lengths, dropout_masks=None):
-    """fwd + CTC loss + bwd (tfsr/trainer_sr.py:56-71).  The CTC loss itself (tf.nn.ctc_loss in
-    the reference, blank = class_n - 1, SURVEY.md 8f "next-2") is taken from torch here; the
-    routing forward/backward run in the CUDA library.  Returns (loss, grads, d_emb)."""
+    """fwd + CTC loss + bwd (tfsr/trainer_sr.py:56-71), all in the CUDA library (CTC loss:
+    srf_ctc_loss, blank = class_n - 1).  Returns (summed loss, grads, d_emb)."""
+    from . import training
     logits = self.forward_train(emb, dropout_masks)
-    lt = logits.detach().requires_grad_(True)
-    logp = torch.log_softmax(lt, dim=-1).transpose(0, 1)
-    loss = torch.nn.functional.ctc_loss(logp, labels, input_lengths, label_lengths,
-                                        blank=self.class_n - 1, reduction="sum", zero_infinity=True)
-    loss.backward()
-    grads, d_emb = self.backward(lt.grad)
-    return loss.detach(), grads, d_emb
+    loss, d_logits = training.ctc_loss(logits, labels, input_lengths, label_lengths,
+                                       blank=self.class_n - 1, handle=self.handle)
+    grads, d_emb = self.backward(d_logits)
+    return loss.sum(), grads, d_emb
 
 
 # ----------------------------------------------------------------------------------------

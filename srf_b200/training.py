@@ -1,0 +1,98 @@
+"""Training-step pieces around the routing stack, all running in the
+CUDA library: greedy CTC decode, CTC loss + gradient, Adam with the reference's warm-up schedule.
+
+Reference: tfsr/trainer_sr.py:56-71 (train step), :133-134 (blank = class_n - 1),
+tfsr/helper/train_helper.py:32-68 (CustomSchedule, Adam)."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, routing
+
+
+def _stream(dev):
+  return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _i32(x, dev):
+  return torch.as_tensor(x).to(device=dev, dtype=torch.int32).contiguous()
+
+
+def ctc_greedy_decode(logits, frame_lengths, blank: Optional[int] = None,
+                      handle: Optional[routing.Handle] = None) -> List[List[int]]:
+  """logits [B,S,C] -> label id lists (argmax, collapse repeats, drop blank = C-1 by default)."""
+  logits = routing.as_device_tensor(logits)
+  h = handle or routing.default_handle(logits.device)
+  B, S, C = logits.shape
+  blank = C - 1 if blank is None else blank
+  lens = _i32(frame_lengths, logits.device)
+  ids = torch.empty((B, S), dtype=torch.int32, device=logits.device)
+  n = torch.empty((B,), dtype=torch.int32, device=logits.device)
+  rc = h.lib.srf_ctc_greedy_decode(h._h, routing._ptr(logits), routing._ptr(lens), B, S, C, blank,
+                                   routing._ptr(ids), routing._ptr(n), _stream(logits.device))
+  _lib.check(h.lib, h._h, rc, "srf_ctc_greedy_decode")
+  ids, n = ids.cpu(), n.cpu()
+  return [ids[b, :int(n[b])].tolist() for b in range(B)]
+
+
+def ctc_loss(logits, labels, input_lengths, label_lengths, blank: Optional[int] = None,
+             grad_scale: float = 1.0, handle: Optional[routing.Handle] = None):
+  """-> (per-utterance loss [B], d_logits [B,S,C] = grad_scale * dloss/dlogits)."""
+  logits = routing.as_device_tensor(logits)
+  h = handle or routing.default_handle(logits.device)
+  dev = logits.device
+  B, S, C = logits.shape
+  blank = C - 1 if blank is None else blank
+  labels = _i32(labels, dev)
+  if labels.dim() != 2 or labels.shape[0] != B:
+    raise ValueError("labels must be [B, Lmax]")
+  Lmax = max(1, labels.shape[1])
+  if labels.shape[1] == 0:
+    labels = torch.zeros((B, 1), dtype=torch.int32, device=dev)
+  in_l, lab_l = _i32(input_lengths, dev), _i32(label_lengths, dev)
+  loss = torch.empty((B,), dtype=torch.float32, device=dev)
+  d_logits = torch.empty((B, S, C), dtype=torch.float32, device=dev)
+  rc = h.lib.srf_ctc_loss(h._h, routing._ptr(logits), routing._ptr(labels), routing._ptr(in_l),
+                          routing._ptr(lab_l), B, S, C, Lmax, blank, float(grad_scale),
+                          routing._ptr(loss), routing._ptr(d_logits), _stream(dev))
+  _lib.check(h.lib, h._h, rc, "srf_ctc_loss")
+  return loss, d_logits
+
+
+def warmup_lr(step: int, k: float, d_model: float, warmup_steps: float, max_lr: float = 10.0) -> float:
+  """CustomSchedule.__call__ (train_helper.py:52-56): min(k * d_model^-0.5 * min(step^-0.5,
+  step * warmup^-1.5), max_lr)."""
+  step = float(step)
+  return min(k * d_model ** -0.5 * min(step ** -0.5, step * warmup_steps ** -1.5), max_lr)
+
+
+class FlatAdam:
+  """tf.keras Adam over one flat fp32 buffer (parameters are views into it), so that a training
+  step is one gradient all-reduce + one fused update."""
+
+  def __init__(self, params: Sequence[torch.Tensor], beta1=0.9, beta2=0.98, eps=1e-9,
+               handle: Optional[routing.Handle] = None):
+    dev = params[0].device
+    self.h = handle or routing.default_handle(dev)
+    self.sizes = [p.numel() for p in params]
+    self.flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+    self.m = torch.zeros_like(self.flat)
+    self.v = torch.zeros_like(self.flat)
+    self.beta1, self.beta2, self.eps, self.step_count = beta1, beta2, eps, 0
+    self.views, off = [], 0
+    for p, n in zip(params, self.sizes):
+      self.views.append(self.flat[off:off + n].view(p.shape))
+      off += n
+
+  def step(self, flat_grad: torch.Tensor, lr: float):
+    if flat_grad.numel() != self.flat.numel():
+      raise ValueError("gradient has %d elements, parameters %d" % (flat_grad.numel(), self.flat.numel()))
+    self.step_count += 1
+    g = flat_grad.contiguous()
+    rc = self.h.lib.srf_adam_step(self.h._h, routing._ptr(self.flat), routing._ptr(g), routing._ptr(self.m),
+                                  routing._ptr(self.v), self.flat.numel(), float(lr), self.beta1, self.beta2,
+                                  self.eps, self.step_count, _stream(self.flat.device))
+    _lib.check(self.h.lib, self.h._h, rc, "srf_adam_step")

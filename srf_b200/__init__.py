@@ -6,6 +6,6 @@ Public surface:
     routing          -- tensor-level wrappers of the C-ABI (include/srf_b200.h)
 """
 from . import _lib, routing, training  # noqa: F401
-from .sequence_router import RoutingStack, SequenceRouter, layer_shapes  # noqa: F401
+from .sequence_router import HostPipeline, RoutingStack, SequenceRouter, layer_shapes  # noqa: F401
 
-__all__ = ["routing", "RoutingStack", "SequenceRouter", "layer_shapes"]
+__all__ = ["routing", "training", "RoutingStack", "SequenceRouter", "HostPipeline", "layer_shapes"]

@@ -335,3 +335,55 @@ def routing_as_tensor(x, device):
     else:
       x = torch.as_tensor(x)
   return x.to(device=device, dtype=torch.float32)
+
+
+class HostPipeline:
+  """Host-buffer front door of RoutingStack for serving loops: pinned host primary capsules in,
+  pinned host logits out, with the host->device copy of batch n+1 and the device->host copy of
+  batch n-1 overlapping the routing of batch n (two staging slots, three CUDA streams).
+
+      pipe = HostPipeline(stack, B, S)
+      for n, host_emb in enumerate(batches):        # host_emb: pinned [B,S,PH,PD] fp32
+        pipe.submit(host_emb)
+        if n: use(pipe.result())                     # logits of batch n-1, pinned host tensor
+      use(pipe.result())
+  """
+
+  def __init__(self, stack: "RoutingStack", B: int, S: int):
+    self.stack, dev = stack, stack.device
+    ph, pd = stack.shapes[0][0] // stack.window, stack.shapes[0][3]
+    self.dev_in = [torch.empty(B, S, ph, pd, device=dev) for _ in range(2)]
+    self.dev_out = [torch.empty(B, S, stack.class_n, device=dev) for _ in range(2)]
+    self.host_out = [torch.empty(B, S, stack.class_n).pin_memory() for _ in range(2)]
+    self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    self.ev_in = [torch.cuda.Event() for _ in range(2)]
+    self.ev_c = [torch.cuda.Event() for _ in range(2)]
+    self.ev_out = [torch.cuda.Event() for _ in range(2)]
+    self.n_sub, self.n_res = 0, 0
+
+  def submit(self, host_emb: torch.Tensor):
+    k = self.n_sub & 1
+    compute = torch.cuda.current_stream(self.stack.device)
+    with torch.cuda.stream(self.s_in):
+      if self.n_sub >= 2:
+        self.s_in.wait_event(self.ev_c[k])          # slot's previous routing has consumed dev_in[k]
+      self.dev_in[k].copy_(host_emb, non_blocking=True)
+      self.ev_in[k].record(self.s_in)
+    compute.wait_event(self.ev_in[k])
+    if self.n_sub >= 2:
+      compute.wait_event(self.ev_out[k])            # dev_out[k] has been copied out
+    self.stack.forward(self.dev_in[k], out_logits=self.dev_out[k])
+    self.ev_c[k].record(compute)
+    with torch.cuda.stream(self.s_out):
+      self.s_out.wait_event(self.ev_c[k])
+      self.host_out[k].copy_(self.dev_out[k], non_blocking=True)
+      self.ev_out[k].record(self.s_out)
+    self.n_sub += 1
+
+  def result(self) -> torch.Tensor:
+    if self.n_res >= self.n_sub:
+      raise RuntimeError("no batch in flight")
+    k = self.n_res & 1
+    self.ev_out[k].synchronize()
+    self.n_res += 1
+    return self.host_out[k]

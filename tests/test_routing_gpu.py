@@ -504,3 +504,22 @@ def test_stack_ctc_train_step_grads_match_autograd():
   assert rel_err(grads["ln_output/gamma"], p.lno_gamma.grad) < 5e-4
   assert rel_err(grads["ln_output/beta"], p.lno_beta.grad) < 5e-4
   assert rel_err(d_emb, emb.grad) < 5e-4
+
+
+def test_host_pipeline_matches_direct_forward():
+  from srf_b200 import HostPipeline, RoutingStack
+  stack = RoutingStack(3, 12, 6, 9, 8, 8, 8, 1, 1, 1, True, seed=3)
+  g = torch.Generator().manual_seed(4)
+  batches = [torch.randn(4, 7, 12, 8, generator=g).pin_memory() for _ in range(5)]
+  ref = [stack.forward(b.cuda()).cpu() for b in batches]
+  pipe = HostPipeline(stack, 4, 7)
+  got = []
+  for n, b in enumerate(batches):
+    pipe.submit(b)
+    if n:
+      got.append(pipe.result().clone())
+  got.append(pipe.result().clone())
+  for a, r in zip(got, ref):
+    assert torch.equal(a, r)
+  with pytest.raises(RuntimeError):
+    pipe.result()

@@ -39,6 +39,9 @@ struct srf_handle {
   float* ws[2] = {nullptr, nullptr};
   size_t ws_bytes = 0;
   int force_F = 0, force_C = 0, no_stream = 0, max_stages = 0;
+  float* bwd_ws = nullptr;  // split-mode backward scratch
+  size_t bwd_ws_bytes = 0;
+  int bwd_atomics = 0;
   float* ctc_ws = nullptr;  // alpha workspace of srf_ctc_loss
   size_t ctc_ws_bytes = 0;
   unsigned long long* dbg = nullptr;  // SRF_PHASE_TIMERS=1: per-CTA phase timers of the streaming kernel
@@ -137,6 +140,7 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_FORCE_C")) h->force_C = atoi(s);
   if (const char* s = getenv("SRF_NO_STREAM")) h->no_stream = atoi(s);
   if (const char* s = getenv("SRF_STREAM_STAGES")) h->max_stages = atoi(s);
+  if (const char* s = getenv("SRF_BWD_ATOMICS")) h->bwd_atomics = atoi(s);
   if (const char* s = getenv("SRF_PHASE_TIMERS")) {
     if (atoi(s) > 0 && cudaMalloc((void**)&h->dbg, 1024 * 8 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(h->dbg, 0, 1024 * 8 * sizeof(unsigned long long));
@@ -157,6 +161,7 @@ extern "C" int srf_destroy(srf_handle* h) {
   if (h->ubuf) cudaFree(h->ubuf);
   if (h->dbg) cudaFree(h->dbg);
   if (h->ctc_ws) cudaFree(h->ctc_ws);
+  if (h->bwd_ws) cudaFree(h->bwd_ws);
   for (int i = 0; i < 2; ++i)
     if (h->ws[i]) cudaFree(h->ws[i]);
   delete h;
@@ -760,6 +765,29 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   p.nsteps = L->sdr ? L->S : 1;
   p.ln_eps = L->ln_eps;
   p.length_eps = L->length_eps;
+  // split mode (default): BPTT sweep saves c / g_a / g_t / Vacc, a frame-parallel kernel builds
+  // dW and dbias without atomics.  SRF_BWD_ATOMICS=1 selects the fused atomics variant.
+  p.split = h->bwd_atomics ? 0 : 1;
+  p.OP = 32 * OPL;
+  p.cbuf = p.gabuf = p.gtT = p.vaT = p.dxw = nullptr;
+  if (p.split) {
+    const size_t frames = (size_t)L->B * L->S, R = (size_t)L->iters;
+    const size_t n_c = frames * R * I * p.OP, n_g = frames * R * L->O * T, n_x = frames * I * T;
+    const size_t need = (2 * n_c + 2 * n_g + n_x) * sizeof(float);
+    if (need > h->bwd_ws_bytes) {
+      if (h->bwd_ws) cudaFreeAsync(h->bwd_ws, stream);
+      h->bwd_ws = nullptr;
+      h->bwd_ws_bytes = 0;
+      cudaError_t ea = cudaMallocAsync((void**)&h->bwd_ws, need, stream);
+      if (ea != cudaSuccess) return cuda_fail(h, ea, "backward workspace allocation");
+      h->bwd_ws_bytes = need;
+    }
+    p.cbuf = h->bwd_ws;
+    p.gabuf = p.cbuf + n_c;
+    p.gtT = p.gabuf + n_c;
+    p.vaT = p.gtT + n_g;
+    p.dxw = p.vaT + n_g;
+  }
   {
     KernelSpan span(h, 2, stream);
     srf::launch_ln_head_bwd(p, stream);
@@ -777,6 +805,20 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
     return cuda_fail(h, e, "route_layer_bwd launch");
   }
   h->launches++;
+  if (p.split) {
+    {
+      KernelSpan span(h, 2, stream);
+      srf::launch_dw_from_saved(p, T, stream);
+    }
+    h->launches++;
+    if (p.d_emb) {
+      KernelSpan span(h, 2, stream);
+      srf::launch_fold_dx(p, T, stream);
+      h->launches++;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(h, e, "dw_from_saved / fold_dx launch");
+  }
   h->last_kernel = "ln_head_bwd_kernel + route_layer_bwd_kernel";
   return 0;
 }

@@ -359,6 +359,17 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         }
       }
       __syncthreads();
+      if (p.split) {
+        for (int e = tid; e < E; e += NT) {
+          const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
+          const int j = q * 32 + ln;
+          if (j < O) {
+            const size_t o = (((size_t)frame * R + r) * O + j) * T + k;
+            p.gtT[o] = gt[e];
+            p.vaT[o] = vacc[r * E + e];
+          }
+        }
+      }
       float va[OPL][T], gtr[OPL][T], gv_acc[OPL][T];
 #pragma unroll
       for (int q = 0; q < OPL; ++q)
@@ -423,13 +434,18 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         for (int q = 0; q < OPL; ++q) {
           const int jp = q * 32 + lane;
           const float ga = c[q] * (gc[q] - cg);
+          if (p.split) {
+            const size_t o = (((size_t)frame * R + r) * I + i) * OP + jp;
+            p.cbuf[o] = c[q];
+            p.gabuf[o] = ga;
+          }
 #pragma unroll
           for (int k = 0; k < T; ++k) {
             const float gu = c[q] * gtr[q][k] + ga * va[q][k];
             gv_acc[q][k] = fmaf(ga, u[q][k], gv_acc[q][k]);
             if (jp < O && k < D) {
-              atomicAdd(p.dbias + ((size_t)i * O + jp) * D + k, gu);
               float* dWrow = p.dW + (((size_t)i * O + jp) * D + k) * p.d;
+              if (!p.split) atomicAdd(p.dbias + ((size_t)i * O + jp) * D + k, gu);
 #pragma unroll
               for (int c4 = 0; c4 < T4; ++c4) {
                 const float4 x4 = xrow[c4];
@@ -440,7 +456,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
                 for (int li = 0; li < 4; ++li) {
                   const int l = c4 * 4 + li;
                   if (l < p.d) {
-                    atomicAdd(dWrow + l, gu * xv[li]);
+                    if (!p.split) atomicAdd(dWrow + l, gu * xv[li]);
                     dx[l] = fmaf(gu, wv[li], dx[l]);
                   }
                 }
@@ -448,7 +464,27 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
             }
           }
         }
-        if (p.d_emb != nullptr) {
+        if (p.split) {
+          // sum dx over the lanes with a transposing butterfly: 31 shuffles, lane l ends up with
+          // the total of dx[l]
+          float v32[32];
+#pragma unroll
+          for (int l = 0; l < 32; ++l) v32[l] = l < T ? dx[l] : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int m = 0; m < o; ++m) {
+              const float send = up ? v32[m] : v32[m + o];
+              const float keep = up ? v32[m + o] : v32[m];
+              v32[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          if (lane < T) {
+            float* dst = p.dxw + ((size_t)frame * I + i) * T + lane;
+            *dst = (r == R - 1) ? v32[0] : *dst + v32[0];
+          }
+        } else if (p.d_emb != nullptr) {
           const int w = i / p.H, hc = i - w * p.H;
           const int src = sf - p.lpad + w;
 #pragma unroll
@@ -475,6 +511,100 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
     }
     // gacc now holds dL/dVacc_0 = the BPTT carry into the previous frame (SDR)
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// split mode, phase B: dW[i,j,k,l] = sum_f sum_r (c g_t[k] + g_a Vacc[k]) x[l],
+// dbias[i,j,k] = sum_f sum_r (c g_t[k] + g_a Vacc[k]).  One CTA per (i, j), one thread per (k, l),
+// the sum over all frames stays in a register: no atomics.
+// ---------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T* T) dw_from_saved_kernel(const BwdParams p) {
+  constexpr int FT = 32;  // frames per shared-memory tile
+  extern __shared__ float sm[];
+  const int R = p.iters, O = p.O, I = p.I;
+  const int OP = p.OP;
+  float* gts = sm;                 // [FT][R][T]
+  float* vas = gts + FT * R * T;   // [FT][R][T]
+  float* xs = vas + FT * R * T;    // [FT][T]
+  float* cs = xs + FT * T;         // [FT][R]
+  float* gas = cs + FT * R;        // [FT][R]
+  const int j = blockIdx.x, i = blockIdx.y;
+  const int tid = threadIdx.x, k = tid / T, l = tid % T;
+  const int w = i / p.H, hc = i - w * p.H;
+  const long long frames = (long long)p.B * p.S;
+  float acc = 0.f, accb = 0.f;
+  for (long long f0 = 0; f0 < frames; f0 += FT) {
+    const int nf = (int)((frames - f0) < FT ? (frames - f0) : FT);
+    for (int e = tid; e < nf * R * T; e += T * T) {
+      const int kk = e % T, fr = e / T;  // fr = ft*R + r
+      const size_t o = (((size_t)f0 * R + fr) * O + j) * T + kk;
+      gts[e] = p.gtT[o];
+      vas[e] = p.vaT[o];
+    }
+    for (int e = tid; e < nf * T; e += T * T) {
+      const int ll = e % T, ft = e / T;
+      const long long f = f0 + ft;
+      const int b = (int)(f / p.S), s = (int)(f % p.S);
+      const int src = s - p.lpad + w;
+      float v = 0.f;
+      if (ll < p.d && src >= 0 && src < p.S) v = p.emb[(((long long)b * p.S + src) * p.H + hc) * p.d + ll];
+      xs[e] = v;
+    }
+    for (int e = tid; e < nf * R; e += T * T) {
+      const size_t o = (((size_t)f0 * R + e) * I + i) * OP + j;
+      cs[e] = p.cbuf[o];
+      gas[e] = p.gabuf[o];
+    }
+    __syncthreads();
+    for (int fr = 0; fr < nf * R; ++fr) {
+      const float gu = fmaf(cs[fr], gts[fr * T + k], gas[fr] * vas[fr * T + k]);
+      acc = fmaf(gu, xs[(fr / R) * T + l], acc);
+      accb += gu;
+    }
+    __syncthreads();
+  }
+  if (k < p.D && l < p.d) p.dW[(((size_t)i * O + j) * p.D + k) * p.d + l] += acc;
+  if (k < p.D && l == 0) p.dbias[((size_t)i * O + j) * p.D + k] += accb;
+}
+
+void launch_dw_from_saved(const BwdParams& p, int T, cudaStream_t stream) {
+  const int FT = 32, R = p.iters;
+  const size_t smem = sizeof(float) * ((size_t)2 * FT * R * T + FT * T + 2 * FT * R);
+  dim3 grid(p.O, p.I);
+  if (T == 8) dw_from_saved_kernel<8><<<grid, 64, smem, stream>>>(p);
+  else if (T == 16) dw_from_saved_kernel<16><<<grid, 256, smem, stream>>>(p);
+  else if (T == 20) dw_from_saved_kernel<20><<<grid, 400, smem, stream>>>(p);
+  else dw_from_saved_kernel<32><<<grid, 1024, smem, stream>>>(p);
+}
+
+// d_emb[b,s',h,l] += sum_w dxw[(b, s'+lpad-w), w*H+h, l]   (fold the window back)
+__global__ void fold_dx_kernel(const BwdParams p, int T) {
+  const long long n = (long long)p.B * p.S * p.H * p.d;
+  const int window = p.I / p.H;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(e % p.d);
+    long long q = e / p.d;
+    const int hc = (int)(q % p.H);
+    q /= p.H;
+    const int s = (int)(q % p.S);
+    const int b = (int)(q / p.S);
+    float acc = 0.f;
+    for (int w = 0; w < window; ++w) {
+      const int sf = s + p.lpad - w;
+      if (sf >= 0 && sf < p.S)
+        acc += p.dxw[(((long long)b * p.S + sf) * p.I + w * p.H + hc) * T + l];
+    }
+    p.d_emb[e] += acc;
+  }
+}
+
+void launch_fold_dx(const BwdParams& p, int T, cudaStream_t stream) {
+  const long long n = (long long)p.B * p.S * p.H * p.d;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fold_dx_kernel<<<blocks, 256, 0, stream>>>(p, T);
 }
 
 template <int T, int OPL>

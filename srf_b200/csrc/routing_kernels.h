@@ -58,7 +58,19 @@ struct BwdParams {
   int B, S, H, d, O, D, I;
   int lpad, iters, sdr, mask0, nsteps;
   float ln_eps, length_eps;
+  // split mode (no per-element atomics): the BPTT sweep stores, per frame and pass, the coupling
+  // coefficients c[i,j], the logit gradients g_a[i,j] and the vectors g_t[j,:], Vacc[j,:]; the
+  // frame-parallel dW kernel rebuilds g_u = c g_t + g_a Vacc from them.
+  int split;
+  int OP;        // padded output capsules (32 * OPL of the BPTT kernel)
+  float* cbuf;   // [frames][R][I][OP]
+  float* gabuf;  // [frames][R][I][OP]
+  float* gtT;    // [frames][R][O][T]
+  float* vaT;    // [frames][R][O][T]
+  float* dxw;    // [frames][I][T]   dL/dx of the windowed input
 };
+void launch_dw_from_saved(const BwdParams& p, int T, cudaStream_t stream);
+void launch_fold_dx(const BwdParams& p, int T, cudaStream_t stream);
 void launch_ln_head_bwd(const BwdParams& p, cudaStream_t stream);
 cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int nchains,
                                    cudaStream_t stream);

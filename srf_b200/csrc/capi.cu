@@ -724,18 +724,36 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   if (L->iters > 8) return fail(h, -3, "backward supports iters <= 8");
   const int window = L->lpad + L->rpad + 1;
   const int I = window * L->H;
-  const int m = L->D > L->d ? L->D : L->d;
-  const int T = m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 20 ? 20 : 32));
+  const int um = L->uhat_mode == SRF_UHAT_FP32 ? 0 : (L->uhat_mode == SRF_UHAT_BF16 ? 1 : 2);
   const int OPL = L->O <= 32 ? 1 : (L->O <= 64 ? 2 : 4);
+  if (um != 0 && h->bwd_atomics)
+    return fail(h, -4, "SRF_BWD_ATOMICS=1 supports uhat_mode FP32 only");
+  int T;
+  const PackedWeights* pw = nullptr;
+  if (um == 0) {
+    // exact mode: the BPTT sweep recomputes u_hat in FP32 from the packed weights
+    const int m = L->D > L->d ? L->D : L->d;
+    T = m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 20 ? 20 : 32));
+    rc = get_packed(h, L, I, T, 32 * OPL, stream, &pw);
+    if (rc) return rc;
+  } else {
+    // tensor path: u_hat of the whole layer by the tcgen05 GEMM, streamed by the BPTT sweep
+    UhatGeom g;
+    rc = uhat_geometry(h, L, &g);
+    if (rc) return rc;
+    T = g.T;
+    rc = compute_uhat(h, L, g, stream);
+    if (rc) return rc;
+  }
   if ((T >= 16 && OPL > 2) || (T == 32 && OPL > 1))
     return fail(h, -3, "backward: O=%d with D=%d is not instantiated", L->O, L->D);
-  const PackedWeights* pw = nullptr;
-  rc = get_packed(h, L, I, T, 32 * OPL, stream, &pw);
-  if (rc) return rc;
   srf::BwdParams p;
   p.emb = L->emb;
-  p.Wp = pw->Wp;
-  p.Bp = pw->Bp;
+  p.Wp = pw ? pw->Wp : nullptr;
+  p.Bp = pw ? pw->Bp : nullptr;
+  p.W = L->W;
+  p.u = um != 0 ? h->ubuf : nullptr;
+  p.halfB = (L->B + 1) / 2;
   p.ln_gamma = L->ln_gamma;
   p.ln_beta = L->ln_beta;
   p.dropout_mask = L->dropout_mask;
@@ -765,15 +783,24 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   p.nsteps = L->sdr ? L->S : 1;
   p.ln_eps = L->ln_eps;
   p.length_eps = L->length_eps;
-  // split mode (default): BPTT sweep saves c / g_a / g_t / Vacc, a frame-parallel kernel builds
-  // dW and dbias without atomics.  SRF_BWD_ATOMICS=1 selects the fused atomics variant.
+  // split mode (default): the BPTT sweep saves c / g_a / g_t / Vacc, the frame-parallel phase B
+  // builds dW, dbias and dx without atomics.  SRF_BWD_ATOMICS=1 selects the fused atomics variant.
   p.split = h->bwd_atomics ? 0 : 1;
   p.OP = 32 * OPL;
-  p.cbuf = p.gabuf = p.gtT = p.vaT = p.dxw = nullptr;
+  p.Tu = T;
+  p.dp = (L->d + 3) & ~3;
+  p.FS = 1;
+  p.fps = 0;
+  p.cbuf = p.gabuf = p.gtT = p.vaT = p.dxw = p.dwp = nullptr;
   if (p.split) {
+    p.FS = srf::dwdx_frame_splits(p, h->max_smem, h->num_sms);
+    if (p.FS <= 0) return fail(h, -3, "backward phase B does not fit in shared memory (D=%d, d=%d)", L->D, L->d);
     const size_t frames = (size_t)L->B * L->S, R = (size_t)L->iters;
-    const size_t n_c = frames * R * I * p.OP, n_g = frames * R * L->O * T, n_x = frames * I * T;
-    const size_t need = (2 * n_c + 2 * n_g + n_x) * sizeof(float);
+    p.fps = (int)((frames + p.FS - 1) / p.FS);
+    const size_t n_c = frames * R * I * p.OP, n_g = frames * R * L->O * T;
+    const size_t n_x = frames * I * OPL * p.dp;
+    const size_t n_w = (size_t)p.FS * I * L->O * L->D * (L->d + 1);
+    const size_t need = (2 * n_c + 2 * n_g + n_x + n_w) * sizeof(float);
     if (need > h->bwd_ws_bytes) {
       if (h->bwd_ws) cudaFreeAsync(h->bwd_ws, stream);
       h->bwd_ws = nullptr;
@@ -787,6 +814,7 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
     p.gtT = p.gabuf + n_c;
     p.vaT = p.gtT + n_g;
     p.dxw = p.vaT + n_g;
+    p.dwp = p.dxw + n_x;
   }
   {
     KernelSpan span(h, 2, stream);
@@ -797,8 +825,19 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   if (e != cudaSuccess) return cuda_fail(h, e, "ln_head_bwd launch");
   const long long nchains = L->sdr ? L->B : (long long)L->B * L->S;
   {
+    // cluster split over the input capsules when there are fewer chains than SMs (SDR)
+    const int nw = srf::route_layer_bwd_warps(um);
+    int C = pow2_floor(h->num_sms / nchains > 0 ? (int)(h->num_sms / nchains) : 1);
+    if (C > 8) C = 8;
+    while (C > 1 && (I + C - 1) / C < nw / 2) C /= 2;
+    if (h->force_C > 0 && h->force_C <= 8) C = h->force_C;
+    if (!p.split) C = 1;
+    p.C = C;
+    p.Ic = (I + C - 1) / C;
+  }
+  {
     KernelSpan span(h, 2, stream);
-    e = srf::launch_route_layer_bwd(p, T, OPL, (int)nchains, stream);
+    e = srf::launch_route_layer_bwd(p, T, OPL, um, (int)nchains, stream);
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -808,16 +847,20 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   if (p.split) {
     {
       KernelSpan span(h, 2, stream);
-      srf::launch_dw_from_saved(p, T, stream);
+      e = srf::launch_dwdx_from_saved(p, h->max_smem, stream);
     }
-    h->launches++;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return cuda_fail(h, e, "dwdx_from_saved launch");
+    }
+    h->launches += 2;
     if (p.d_emb) {
       KernelSpan span(h, 2, stream);
-      srf::launch_fold_dx(p, T, stream);
+      srf::launch_fold_dx(p, stream);
       h->launches++;
     }
     e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(h, e, "dw_from_saved / fold_dx launch");
+    if (e != cudaSuccess) return cuda_fail(h, e, "fold_dx launch");
   }
   h->last_kernel = "ln_head_bwd_kernel + route_layer_bwd_kernel";
   return 0;

@@ -21,10 +21,13 @@
 //   dbias += g_u;  dW[i,j,k,l] += g_u[j,k] x[i,l];  dx[i,l] += sum_{j,k} g_u[j,k] W[i,j,k,l]
 // (SURVEY.md appendix B for R = 1.)  Parameter gradients are accumulated with fp32 atomics.
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "routing_kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace srf {
 
@@ -40,6 +43,8 @@ __device__ __forceinline__ float bw_sum(float v) {
   return v;
 }
 constexpr int BW_MAX_ITERS = 8;
+#define SRF_BWD_NW_BF16 16
+#define SRF_BWD_NW_F32 12
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -191,24 +196,38 @@ void launch_ln_head_bwd(const BwdParams& p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------
-// K_b2: routing backward.  One CTA per chain; warps stride over the input capsules;
-// lane = output capsule (j = q*32 + lane).
+// K_b2: routing backward (BPTT sweep).  One CTA per chain; warps stride over the input
+// capsules; lane = output capsule (j = q*32 + lane).
+//   UM = 0: u_hat recomputed in FP32 from the packed weights (exact mode);
+//   UM = 1/2: u_hat streamed from the tcgen05 GEMM's output (bf16 / fp32 storage, the layout of
+//             uhat_gemm.cu), one-capsule-ahead register prefetch.
+//   SPLIT: store c, g_a, g_t, Vacc for phase B (dwdx_from_saved_kernel) instead of forming
+//          dW / dbias / dx with atomics in this kernel.
 // ---------------------------------------------------------------------------------------
-template <int T, int OPL, int NW>
+template <int T, int OPL, int NW, int UM, bool SPLIT>
 __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParams p) {
   constexpr int OP = 32 * OPL;
   constexpr int T4 = T / 4;
   constexpr int NT = NW * 32;
   constexpr int E = OPL * T * 32;  // (q*T+k)*32+lane
   constexpr float LOG2E = 1.4426950408889634f;
+  constexpr int RAWN = (UM == 1) ? OPL * T4 : (UM == 2 ? 2 * OPL * T4 : 1);
+  static_assert(UM == 0 || SPLIT, "streamed u_hat needs split mode");
 
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chain = blockIdx.x;
+  const int C = p.C;
+  int rank = 0;
+  if (C > 1) rank = (int)cg::this_cluster().block_rank();
+  const int chain = blockIdx.x / C;
   const int I = p.I, O = p.O, D = p.D, R = p.iters;
-  float* xs = smem;                 // [I][T] window-gathered input of the frame
-  float* red = xs + (size_t)I * T;  // [NW][E]
-  float* tr = red + NW * E;         // [R][E]   t_r
+  const int i_lo = rank * p.Ic;
+  const int i_hi = min(I, i_lo + p.Ic);
+  constexpr int PER = (E + NT - 1) / NT;
+  float* xs = smem;                 // [Ic][T] window-gathered input of the frame (UM == 0)
+  float* red = xs + (UM == 0 ? (size_t)p.Ic * T : 0);  // [NW][E]
+  float* tsum = red + NW * E;       // [2][E]   CTA partial for the cluster exchange
+  float* tr = tsum + 2 * E;         // [R][E]   t_r
   float* vacc = tr + BW_MAX_ITERS * E;  // [R+1][E] Vacc_0 .. Vacc_R
   float* gout = vacc + (BW_MAX_ITERS + 1) * E;  // [E] dL/dv of this frame (incl. BPTT carry)
   float* gt = gout + E;             // [E] g_t of the current pass
@@ -219,35 +238,125 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
 
   for (int e = tid; e < E; e += NT) gacc[e] = 0.f;  // BPTT carry into the last frame is zero
   __syncthreads();
+  int par = 0;
+  // dL/dv_raw of a frame and the carried output of the frame before it, fetched one step ahead
+  float nd[PER], nv[PER];
+  auto fetch_frame = [&](int step_) {
+    const int b_ = p.sdr ? chain : chain / p.S;
+    const int sf_ = p.sdr ? step_ : chain % p.S;
+    const long long fr_ = (long long)b_ * p.S + sf_;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = tid + u * NT;
+      const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
+      const int j = q * 32 + ln;
+      const bool ok = e < E && j < O && k < D;
+      nd[u] = ok ? __ldg(p.d_raw + (fr_ * O + j) * D + k) : 0.f;
+      nv[u] = (ok && p.sdr && sf_ > 0) ? __ldg(p.v_raw + ((fr_ - 1) * O + j) * D + k) : 0.f;
+    }
+  };
+  fetch_frame(p.nsteps - 1);
 
   for (int step = p.nsteps - 1; step >= 0; --step) {
     const int b = p.sdr ? chain : chain / p.S;
     const int sf = p.sdr ? step : chain % p.S;
     const long long frame = (long long)b * p.S + sf;
+    // streamed u_hat: frame pair index and which member of the pair this chain is
+    const long long gg = (long long)sf * p.halfB + (b >> 1);
+    const bool mem1 = (b & 1) != 0;
+    const size_t ustride_i = (size_t)OPL * T4 * 128 * 2;  // elements per (pair, i)
+    auto load_raw = [&](int i, uint4(&dst)[RAWN]) {
+      if (UM == 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const uint16_t*>(p.u) + ((size_t)gg * I + i) * ustride_i);
+#pragma unroll
+        for (int m = 0; m < OPL * T4; ++m) dst[m] = __ldg(src + m * 32 + lane);
+      } else if (UM == 2) {
+        const uint4* src = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const float*>(p.u) + ((size_t)gg * I + i) * ustride_i);
+#pragma unroll
+        for (int m = 0; m < OPL * T4; ++m) {
+          dst[(2 * m) % RAWN] = __ldg(src + (m * 32 + lane) * 2);
+          dst[(2 * m + 1) % RAWN] = __ldg(src + (m * 32 + lane) * 2 + 1);
+        }
+      }
+    };
+    // element (k_in, member) of chunk m = (q, k4) sits at 2*k_in + member
+    auto unpack = [&](const uint4(&raw)[RAWN], float(&u)[OPL][T]) {
+#pragma unroll
+      for (int q = 0; q < OPL; ++q)
+#pragma unroll
+        for (int k4 = 0; k4 < T4; ++k4) {
+          const int m = q * T4 + k4;
+          if (UM == 1) {
+            const uint32_t w[4] = {raw[m % RAWN].x, raw[m % RAWN].y, raw[m % RAWN].z, raw[m % RAWN].w};
+#pragma unroll
+            for (int kin = 0; kin < 4; ++kin)
+              u[q][k4 * 4 + kin] = __uint_as_float(mem1 ? (w[kin] & 0xffff0000u) : (w[kin] << 16));
+          } else {
+            const uint4 r0 = raw[(2 * m) % RAWN], r1 = raw[(2 * m + 1) % RAWN];
+            u[q][k4 * 4 + 0] = __uint_as_float(mem1 ? r0.y : r0.x);
+            u[q][k4 * 4 + 1] = __uint_as_float(mem1 ? r0.w : r0.z);
+            u[q][k4 * 4 + 2] = __uint_as_float(mem1 ? r1.y : r1.x);
+            u[q][k4 * 4 + 3] = __uint_as_float(mem1 ? r1.w : r1.z);
+          }
+        }
+    };
+    auto compute_u = [&](int i, float(&u)[OPL][T]) {
+      const float4* xrow = reinterpret_cast<const float4*>(xs) + (size_t)(i - i_lo) * T4;
+#pragma unroll
+      for (int q = 0; q < OPL; ++q) {
+        const int jp = q * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+          float acc = Bp[(size_t)(i * T + k) * OP + jp];
+#pragma unroll
+          for (int c = 0; c < T4; ++c) {
+            const float4 w4 = Wp[((size_t)(i * T + k) * T4 + c) * OP + jp];
+            const float4 x4 = xrow[c];
+            acc = fmaf(w4.x, x4.x, acc);
+            acc = fmaf(w4.y, x4.y, acc);
+            acc = fmaf(w4.z, x4.z, acc);
+            acc = fmaf(w4.w, x4.w, acc);
+          }
+          u[q][k] = acc;
+        }
+      }
+    };
+
     // window gather
-    for (int idx = tid; idx < I * T; idx += NT) {
-      const int l = idx % T, i = idx / T;
+    for (int idx = tid; UM == 0 && idx < (i_hi - i_lo) * T; idx += NT) {
+      const int l = idx % T, i = i_lo + idx / T;
       float v = 0.f;
       if (l < p.d) {
         const int w = i / p.H, hc = i - w * p.H;
         const int src = sf - p.lpad + w;
         if (src >= 0 && src < p.S) v = p.emb[(((long long)b * p.S + src) * p.H + hc) * p.d + l];
       }
-      xs[i * T + l] = v;
+      xs[idx] = v;
     }
     // g_out = dL/d v_raw[frame] + carry; Vacc_0 = previous frame's output (SDR) or 0
-    for (int e = tid; e < E; e += NT) {
-      const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
-      const int j = q * 32 + ln;
-      const bool ok = j < O && k < D;
-      float g = ok ? p.d_raw[(frame * O + j) * D + k] : 0.f;
-      if (p.sdr) g += gacc[e];
-      gout[e] = g;
-      float v0 = 0.f;
-      if (p.sdr && sf > 0 && ok) v0 = p.v_raw[((frame - 1) * O + j) * D + k];
-      vacc[e] = v0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = tid + u * NT;
+      if (e < E) {
+        gout[e] = nd[u] + (p.sdr ? gacc[e] : 0.f);
+        vacc[e] = nv[u];
+      }
     }
     __syncthreads();
+    if (step > 0) fetch_frame(step - 1);
+    // pull the next step's u_hat lines of this warp's capsules into L2 while this step computes
+    if (UM != 0 && step > 0) {
+      constexpr int LINES = (int)(OPL * T4 * 128 * 2 * (UM == 1 ? 2 : 4) / 128);
+      const long long ggn = (long long)(sf - 1) * p.halfB + (b >> 1);
+      for (int i = i_lo + warp; i < i_hi; i += NW) {
+        const char* base = reinterpret_cast<const char*>(p.u) +
+                           ((size_t)ggn * I + i) * (size_t)(OPL * T4 * 128 * 2) * (UM == 1 ? 2 : 4);
+        for (int ln = lane; ln < LINES; ln += 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)ln * 128));
+      }
+    }
 
     // ---------------- forward recompute: t_r, Vacc_r ----------------
     for (int r = 0; r < R; ++r) {
@@ -259,26 +368,19 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           va[q][k] = vacc[r * E + (q * T + k) * 32 + lane];
           ta[q][k] = 0.f;
         }
-      for (int i = warp; i < I; i += NW) {
+      uint4 raw[RAWN];
+      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
+      for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[OPL][T], a[OPL];
-        const float4* xrow = reinterpret_cast<const float4*>(xs) + (size_t)i * T4;
+        if (UM != 0) {
+          unpack(raw, u);
+          if (i + NW < i_hi) load_raw(i + NW, raw);
+        } else {
+          compute_u(i, u);
+        }
 #pragma unroll
         for (int q = 0; q < OPL; ++q) {
           const int jp = q * 32 + lane;
-#pragma unroll
-          for (int k = 0; k < T; ++k) {
-            float acc = Bp[(size_t)(i * T + k) * OP + jp];
-#pragma unroll
-            for (int c = 0; c < T4; ++c) {
-              const float4 w4 = Wp[((size_t)(i * T + k) * T4 + c) * OP + jp];
-              const float4 x4 = xrow[c];
-              acc = fmaf(w4.x, x4.x, acc);
-              acc = fmaf(w4.y, x4.y, acc);
-              acc = fmaf(w4.z, x4.z, acc);
-              acc = fmaf(w4.w, x4.w, acc);
-            }
-            u[q][k] = acc;
-          }
           float acc = 0.f;
 #pragma unroll
           for (int k = 0; k < T; ++k) acc = fmaf(u[q][k], va[q][k], acc);
@@ -309,7 +411,18 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         float acc = 0.f;
 #pragma unroll
         for (int w = 0; w < NW; ++w) acc += red[w * E + e];
-        tr[r * E + e] = acc;
+        if (C > 1) tsum[par * E + e] = acc;
+        else tr[r * E + e] = acc;
+      }
+      if (C > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        for (int e = tid; e < E; e += NT) {
+          float acc = 0.f;
+          for (int rk = 0; rk < C; ++rk) acc += cluster.map_shared_rank(tsum, rk)[par * E + e];
+          tr[r * E + e] = acc;
+        }
+        par ^= 1;
       }
       __syncthreads();
       for (int idx = tid; idx < OPL * 32; idx += NT) {
@@ -359,7 +472,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         }
       }
       __syncthreads();
-      if (p.split) {
+      if (SPLIT && rank == 0) {
         for (int e = tid; e < E; e += NT) {
           const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
           const int j = q * 32 + ln;
@@ -379,26 +492,19 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           gtr[q][k] = gt[(q * T + k) * 32 + lane];
           gv_acc[q][k] = 0.f;
         }
-      for (int i = warp; i < I; i += NW) {
+      uint4 raw[RAWN];
+      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
+      for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[OPL][T], a[OPL];
-        const float4* xrow = reinterpret_cast<const float4*>(xs) + (size_t)i * T4;
+        if (UM != 0) {
+          unpack(raw, u);
+          if (i + NW < i_hi) load_raw(i + NW, raw);
+        } else {
+          compute_u(i, u);
+        }
 #pragma unroll
         for (int q = 0; q < OPL; ++q) {
           const int jp = q * 32 + lane;
-#pragma unroll
-          for (int k = 0; k < T; ++k) {
-            float acc = Bp[(size_t)(i * T + k) * OP + jp];
-#pragma unroll
-            for (int c = 0; c < T4; ++c) {
-              const float4 w4 = Wp[((size_t)(i * T + k) * T4 + c) * OP + jp];
-              const float4 x4 = xrow[c];
-              acc = fmaf(w4.x, x4.x, acc);
-              acc = fmaf(w4.y, x4.y, acc);
-              acc = fmaf(w4.z, x4.z, acc);
-              acc = fmaf(w4.w, x4.w, acc);
-            }
-            u[q][k] = acc;
-          }
           float acc = 0.f;
 #pragma unroll
           for (int k = 0; k < T; ++k) acc = fmaf(u[q][k], va[q][k], acc);
@@ -426,72 +532,61 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           cg = fmaf(c[q], acc, cg);
         }
         cg = bw_sum(cg);
-        // per-lane g_u, dbias, dW; dx needs a sum over output capsules (lanes)
-        float dx[T];
+        if (SPLIT) {
 #pragma unroll
-        for (int l = 0; l < T; ++l) dx[l] = 0.f;
-#pragma unroll
-        for (int q = 0; q < OPL; ++q) {
-          const int jp = q * 32 + lane;
-          const float ga = c[q] * (gc[q] - cg);
-          if (p.split) {
+          for (int q = 0; q < OPL; ++q) {
+            const int jp = q * 32 + lane;
+            const float ga = c[q] * (gc[q] - cg);
             const size_t o = (((size_t)frame * R + r) * I + i) * OP + jp;
             p.cbuf[o] = c[q];
             p.gabuf[o] = ga;
+#pragma unroll
+            for (int k = 0; k < T; ++k) gv_acc[q][k] = fmaf(ga, u[q][k], gv_acc[q][k]);
           }
+        } else {
+          // fused variant: per-lane g_u, dbias, dW with atomics; dx summed over the lanes
+          const float4* xrow = reinterpret_cast<const float4*>(xs) + (size_t)(i - i_lo) * T4;
+          float dx[T];
 #pragma unroll
-          for (int k = 0; k < T; ++k) {
-            const float gu = c[q] * gtr[q][k] + ga * va[q][k];
-            gv_acc[q][k] = fmaf(ga, u[q][k], gv_acc[q][k]);
-            if (jp < O && k < D) {
-              float* dWrow = p.dW + (((size_t)i * O + jp) * D + k) * p.d;
-              if (!p.split) atomicAdd(p.dbias + ((size_t)i * O + jp) * D + k, gu);
+          for (int l = 0; l < T; ++l) dx[l] = 0.f;
 #pragma unroll
-              for (int c4 = 0; c4 < T4; ++c4) {
-                const float4 x4 = xrow[c4];
-                const float4 w4 = Wp[((size_t)(i * T + k) * T4 + c4) * OP + jp];
-                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          for (int q = 0; q < OPL; ++q) {
+            const int jp = q * 32 + lane;
+            const float ga = c[q] * (gc[q] - cg);
 #pragma unroll
-                for (int li = 0; li < 4; ++li) {
-                  const int l = c4 * 4 + li;
-                  if (l < p.d) {
-                    if (!p.split) atomicAdd(dWrow + l, gu * xv[li]);
-                    dx[l] = fmaf(gu, wv[li], dx[l]);
+            for (int k = 0; k < T; ++k) {
+              const float gu = c[q] * gtr[q][k] + ga * va[q][k];
+              gv_acc[q][k] = fmaf(ga, u[q][k], gv_acc[q][k]);
+              if (jp < O && k < D) {
+                float* dWrow = p.dW + (((size_t)i * O + jp) * D + k) * p.d;
+                atomicAdd(p.dbias + ((size_t)i * O + jp) * D + k, gu);
+#pragma unroll
+                for (int c4 = 0; c4 < T4; ++c4) {
+                  const float4 x4 = xrow[c4];
+                  const float4 w4 = Wp[((size_t)(i * T + k) * T4 + c4) * OP + jp];
+                  const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                  const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                  for (int li = 0; li < 4; ++li) {
+                    const int l = c4 * 4 + li;
+                    if (l < p.d) {
+                      atomicAdd(dWrow + l, gu * xv[li]);
+                      dx[l] = fmaf(gu, wv[li], dx[l]);
+                    }
                   }
                 }
               }
             }
           }
-        }
-        if (p.split) {
-          // sum dx over the lanes with a transposing butterfly: 31 shuffles, lane l ends up with
-          // the total of dx[l]
-          float v32[32];
+          if (p.d_emb != nullptr) {
+            const int w = i / p.H, hc = i - w * p.H;
+            const int src = sf - p.lpad + w;
 #pragma unroll
-          for (int l = 0; l < 32; ++l) v32[l] = l < T ? dx[l] : 0.f;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int m = 0; m < o; ++m) {
-              const float send = up ? v32[m] : v32[m + o];
-              const float keep = up ? v32[m + o] : v32[m];
-              v32[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            for (int l = 0; l < T; ++l) {
+              const float s = bw_sum(dx[l]);
+              if (lane == 0 && l < p.d && src >= 0 && src < p.S)
+                atomicAdd(p.d_emb + (((long long)b * p.S + src) * p.H + hc) * p.d + l, s);
             }
-          }
-          if (lane < T) {
-            float* dst = p.dxw + ((size_t)frame * I + i) * T + lane;
-            *dst = (r == R - 1) ? v32[0] : *dst + v32[0];
-          }
-        } else if (p.d_emb != nullptr) {
-          const int w = i / p.H, hc = i - w * p.H;
-          const int src = sf - p.lpad + w;
-#pragma unroll
-          for (int l = 0; l < T; ++l) {
-            const float s = bw_sum(dx[l]);
-            if (lane == 0 && l < p.d && src >= 0 && src < p.S)
-              atomicAdd(p.d_emb + (((long long)b * p.S + src) * p.H + hc) * p.d + l, s);
           }
         }
       }
@@ -502,86 +597,285 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         for (int k = 0; k < T; ++k) red[warp * E + (q * T + k) * 32 + lane] = gv_acc[q][k];
       __syncthreads();
       for (int e = tid; e < E; e += NT) {
-        float acc = gacc[e];
+        float acc = 0.f;
 #pragma unroll
         for (int w = 0; w < NW; ++w) acc += red[w * E + e];
-        gacc[e] = acc;
+        if (C > 1) tsum[par * E + e] = acc;
+        else gacc[e] += acc;
+      }
+      if (C > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        for (int e = tid; e < E; e += NT) {
+          float acc = gacc[e];
+          for (int rk = 0; rk < C; ++rk) acc += cluster.map_shared_rank(tsum, rk)[par * E + e];
+          gacc[e] = acc;
+        }
+        par ^= 1;
       }
       __syncthreads();
     }
     // gacc now holds dL/dVacc_0 = the BPTT carry into the previous frame (SDR)
   }
+  if (C > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's tsum
 }
 
 // ---------------------------------------------------------------------------------------
-// split mode, phase B: dW[i,j,k,l] = sum_f sum_r (c g_t[k] + g_a Vacc[k]) x[l],
-// dbias[i,j,k] = sum_f sum_r (c g_t[k] + g_a Vacc[k]).  One CTA per (i, j), one thread per (k, l),
-// the sum over all frames stays in a register: no atomics.
+// split mode, phase B: frame-parallel dW, dbias and dx from the saved coefficients.
+//   g_u[f,i,j,k] = sum_r c[f,r,i,j] g_t[f,r,j,k] + g_a[f,r,i,j] Vacc[f,r,j,k]   (rank 2 per (i,j))
+//   dW[i,j,k,l] = sum_f g_u x[f,i,l];  dbias[i,j,k] = sum_f g_u;  dx[f,i,l] = sum_jk g_u W[i,j,k,l]
+// grid (I, FS frame splits, 32-capsule chunks of j).  Per tile of FT frames the CTA builds g_u in
+// shared memory once ([ft][k][j], k rows padded to 36 floats so both the float4 row reads of
+// the dW phase and the per-frame reads of the dx phase are conflict-free), then
+//   dW phase: thread (k, l) keeps the sums for all 32 j in registers (l == d is the bias column:
+//             x augmented with a 1), 9 shared loads per 32 FMAs;
+//   dx phase: thread (ft, l quad, part) walks (k, 4 j) units against W[i] held in shared memory.
+// Partial sums per frame split go to dwp and are folded by reduce_dwp_kernel: no atomics, the
+// result is deterministic.
 // ---------------------------------------------------------------------------------------
-template <int T>
-__global__ void __launch_bounds__(T* T) dw_from_saved_kernel(const BwdParams p) {
-  constexpr int FT = 32;  // frames per shared-memory tile
-  extern __shared__ float sm[];
-  const int R = p.iters, O = p.O, I = p.I;
-  const int OP = p.OP;
-  float* gts = sm;                 // [FT][R][T]
-  float* vas = gts + FT * R * T;   // [FT][R][T]
-  float* xs = vas + FT * R * T;    // [FT][T]
-  float* cs = xs + FT * T;         // [FT][R]
-  float* gas = cs + FT * R;        // [FT][R]
-  const int j = blockIdx.x, i = blockIdx.y;
-  const int tid = threadIdx.x, k = tid / T, l = tid % T;
+namespace {
+struct DwdxPlan {
+  int FT, NT, NTc, P, aug;
+  size_t smem;
+};
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
+}  // namespace
+
+size_t dwdx_smem_bytes(int D, int d, int P, int FT) {
+  const int dp = (d + 3) & ~3;
+  return sizeof(float) * ((size_t)32 * D * dp + (size_t)FT * (D * 36 + 4) + round4(FT * (d + 1)) +
+                          (size_t)P * FT * dp);
+}
+
+static bool dwdx_plan(const BwdParams& p, int max_smem, DwdxPlan* pl) {
+  const int D = p.D, d = p.d, dp = (d + 3) & ~3, LQ = dp / 4;
+  pl->aug = D * (d + 1) <= 1024 ? 1 : 0;
+  pl->NTc = pl->aug ? D * (d + 1) : D * d;
+  int NT = (pl->NTc + 31) & ~31;
+  if (NT < 128) NT = 128;
+  pl->NT = NT;
+  for (int FT = 32; FT >= 4; FT >>= 1) {
+    if (FT * LQ > NT) continue;
+    int P = NT / (FT * LQ);
+    if (P > 8) P = 8;
+    const size_t smem = dwdx_smem_bytes(D, d, P, FT);
+    if (smem <= (size_t)max_smem) {
+      pl->FT = FT;
+      pl->P = P;
+      pl->smem = smem;
+      return true;
+    }
+  }
+  return false;
+}
+
+// number of frame splits phase B will use (the caller sizes dwp with it)
+int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms) {
+  DwdxPlan pl;
+  if (!dwdx_plan(p, max_smem, &pl)) return 0;
+  const long long frames = (long long)p.B * p.S;
+  const long long tiles = (frames + pl.FT - 1) / pl.FT;
+  const int per = p.I * (p.OP / 32);
+  long long FS = (4LL * num_sms + per - 1) / per;
+  if (FS > tiles / 4) FS = tiles / 4;
+  if (FS > 32) FS = 32;
+  if (FS < 1) FS = 1;
+  return (int)FS;
+}
+
+template <bool AUG, int MAXT>
+__global__ void __launch_bounds__(MAXT) dwdx_from_saved_kernel(const BwdParams p, int FT, int ftsh,
+                                                                int NTc, int P) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = p.D, d = p.d, dp = p.dp, R = p.iters, O = p.O, I = p.I, OP = p.OP, Tu = p.Tu;
+  const int d1 = d + 1, LQ = dp >> 2, GS = D * 36 + 4, NT = blockDim.x;
+  float* Ws = sm;                          // [32][D][dp]
+  float* gus = Ws + 32 * D * dp;           // [FT][GS]: g_u[ft][k][j] at k*36 + j
+  float* xs = gus + FT * GS;               // [FT][d+1]
+  float* dxs = xs + round4(FT * d1);       // [P][FT][dp]
+  const int i = blockIdx.x, fs = blockIdx.y, q = blockIdx.z, OPL = gridDim.z;
+  const int jbase = q * 32;
+  const int nj = (O - jbase) < 32 ? (O - jbase) : 32;
+  const int tid = threadIdx.x;
   const int w = i / p.H, hc = i - w * p.H;
   const long long frames = (long long)p.B * p.S;
-  float acc = 0.f, accb = 0.f;
-  for (long long f0 = 0; f0 < frames; f0 += FT) {
-    const int nf = (int)((frames - f0) < FT ? (frames - f0) : FT);
-    for (int e = tid; e < nf * R * T; e += T * T) {
-      const int kk = e % T, fr = e / T;  // fr = ft*R + r
-      const size_t o = (((size_t)f0 * R + fr) * O + j) * T + kk;
-      gts[e] = p.gtT[o];
-      vas[e] = p.vaT[o];
-    }
-    for (int e = tid; e < nf * T; e += T * T) {
-      const int ll = e % T, ft = e / T;
-      const long long f = f0 + ft;
-      const int b = (int)(f / p.S), s = (int)(f % p.S);
-      const int src = s - p.lpad + w;
+  const long long f_lo = (long long)fs * p.fps;
+  const long long f_hi = (f_lo + p.fps) < frames ? (f_lo + p.fps) : frames;
+
+  for (int e = tid; e < 32 * D * dp; e += NT) {
+    const int l = e % dp, jk = e / dp, k = jk % D, j = jk / D;
+    float v = 0.f;
+    if (j < nj && l < d) v = p.W[(((size_t)i * O + jbase + j) * D + k) * d + l];
+    Ws[e] = v;
+  }
+  const unsigned magicD = (65536u + D - 1) / D;  // e / D for e < 1056, D <= 32
+  const int lw = AUG ? d1 : d;
+  const bool dw_thread = tid < NTc;
+  const int k_dw = tid / lw, l_dw = tid - k_dw * lw;
+  float acc[32], accb[AUG ? 1 : 32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < (AUG ? 1 : 32); ++j) accb[j] = 0.f;
+  const int ft_dx = tid & (FT - 1), rest = tid >> ftsh;
+  const int part = rest / LQ, lq = rest - part * LQ;
+  const bool dx_thread = part < P;
+
+  for (long long f0 = f_lo; f0 < f_hi; f0 += FT) {
+    const int nf = (int)((f_hi - f0) < FT ? (f_hi - f0) : FT);
+    // (a) window-gathered x of capsule i for the tile (+ the bias column of ones)
+    for (int e = tid; e < FT * d1; e += NT) {
+      const int ft = e / d1, l = e - ft * d1;
       float v = 0.f;
-      if (ll < p.d && src >= 0 && src < p.S) v = p.emb[(((long long)b * p.S + src) * p.H + hc) * p.d + ll];
+      if (ft < nf) {
+        if (l == d) {
+          v = 1.f;
+        } else {
+          const long long f = f0 + ft;
+          const int b = (int)(f / p.S), s = (int)(f - (long long)b * p.S);
+          const int src = s - p.lpad + w;
+          if (src >= 0 && src < p.S) v = p.emb[(((long long)b * p.S + src) * p.H + hc) * d + l];
+        }
+      }
       xs[e] = v;
     }
-    for (int e = tid; e < nf * R; e += T * T) {
-      const size_t o = (((size_t)f0 * R + e) * I + i) * OP + j;
-      cs[e] = p.cbuf[o];
-      gas[e] = p.gabuf[o];
+    // (b) g_u of the tile: each thread owns (j, k) elements and walks the frames eight at a time
+    // with all 32 loads of a group in flight
+    for (int e2 = tid; e2 < 32 * D; e2 += NT) {
+      const int j = (int)(((unsigned)e2 * magicD) >> 16), k = e2 - j * D;
+      const bool jok = j < nj;
+      for (int ft0 = 0; ft0 < FT; ft0 += 8) {
+        float g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[u] = 0.f;
+        for (int r = 0; r < R; ++r) {
+          float cv[8], gav[8], gtv[8], vav[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int ft = ft0 + u;
+            const bool ok = jok && ft < nf;
+            const size_t fr = (size_t)(f0 + (ok ? ft : 0)) * R + r;
+            const size_t co = (fr * I + i) * OP + jbase + (ok ? j : 0);
+            const size_t go = (fr * O + jbase + (ok ? j : 0)) * Tu + k;
+            cv[u] = ok ? __ldg(p.cbuf + co) : 0.f;
+            gav[u] = ok ? __ldg(p.gabuf + co) : 0.f;
+            gtv[u] = ok ? __ldg(p.gtT + go) : 0.f;
+            vav[u] = ok ? __ldg(p.vaT + go) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) g[u] = fmaf(cv[u], gtv[u], fmaf(gav[u], vav[u], g[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (ft0 + u < FT) gus[(ft0 + u) * GS + k * 36 + j] = g[u];
+      }
     }
     __syncthreads();
-    for (int fr = 0; fr < nf * R; ++fr) {
-      const float gu = fmaf(cs[fr], gts[fr * T + k], gas[fr] * vas[fr * T + k]);
-      acc = fmaf(gu, xs[(fr / R) * T + l], acc);
-      accb += gu;
+    // (c) dW / dbias
+    if (dw_thread) {
+      for (int ft = 0; ft < FT; ++ft) {
+        const float xv = xs[ft * d1 + l_dw];
+        const float4* row = reinterpret_cast<const float4*>(gus + ft * GS + k_dw * 36);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 g4 = row[j4];
+          acc[j4 * 4 + 0] = fmaf(g4.x, xv, acc[j4 * 4 + 0]);
+          acc[j4 * 4 + 1] = fmaf(g4.y, xv, acc[j4 * 4 + 1]);
+          acc[j4 * 4 + 2] = fmaf(g4.z, xv, acc[j4 * 4 + 2]);
+          acc[j4 * 4 + 3] = fmaf(g4.w, xv, acc[j4 * 4 + 3]);
+          if (!AUG && l_dw == 0) {
+            accb[(j4 * 4 + 0) % (AUG ? 1 : 32)] += g4.x;
+            accb[(j4 * 4 + 1) % (AUG ? 1 : 32)] += g4.y;
+            accb[(j4 * 4 + 2) % (AUG ? 1 : 32)] += g4.z;
+            accb[(j4 * 4 + 3) % (AUG ? 1 : 32)] += g4.w;
+          }
+        }
+      }
+    }
+    // (d) dx partials
+    if (dx_thread) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* grow = gus + ft_dx * GS;
+      for (int un = part; un < 8 * D; un += P) {
+        const int k = un >> 3, j4 = un & 7;
+        const float4 g4 = *reinterpret_cast<const float4*>(grow + k * 36 + j4 * 4);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 w4 =
+              *reinterpret_cast<const float4*>(Ws + ((size_t)(j4 * 4 + jj) * D + k) * dp + lq * 4);
+          a.x = fmaf(gv[jj], w4.x, a.x);
+          a.y = fmaf(gv[jj], w4.y, a.y);
+          a.z = fmaf(gv[jj], w4.z, a.z);
+          a.w = fmaf(gv[jj], w4.w, a.w);
+        }
+      }
+      *reinterpret_cast<float4*>(dxs + ((size_t)part * FT + ft_dx) * dp + lq * 4) = a;
     }
     __syncthreads();
+    for (int e = tid; e < nf * dp; e += NT) {
+      const int ft = e / dp, l = e - ft * dp;
+      float s = 0.f;
+      for (int pp = 0; pp < P; ++pp) s += dxs[((size_t)pp * FT + ft) * dp + l];
+      p.dxw[((((size_t)(f0 + ft)) * I + i) * OPL + q) * dp + l] = s;
+    }
   }
-  if (k < p.D && l < p.d) p.dW[(((size_t)i * O + j) * p.D + k) * p.d + l] += acc;
-  if (k < p.D && l == 0) p.dbias[((size_t)i * O + j) * p.D + k] += accb;
+  if (dw_thread && k_dw < D) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nj) {
+        const size_t o = ((((size_t)fs * I + i) * O + jbase + j) * D + k_dw) * d1;
+        p.dwp[o + l_dw] = acc[j];
+        if (!AUG && l_dw == 0) p.dwp[o + d] = accb[j % (AUG ? 1 : 32)];
+      }
+  }
 }
 
-void launch_dw_from_saved(const BwdParams& p, int T, cudaStream_t stream) {
-  const int FT = 32, R = p.iters;
-  const size_t smem = sizeof(float) * ((size_t)2 * FT * R * T + FT * T + 2 * FT * R);
-  dim3 grid(p.O, p.I);
-  if (T == 8) dw_from_saved_kernel<8><<<grid, 64, smem, stream>>>(p);
-  else if (T == 16) dw_from_saved_kernel<16><<<grid, 256, smem, stream>>>(p);
-  else if (T == 20) dw_from_saved_kernel<20><<<grid, 400, smem, stream>>>(p);
-  else dw_from_saved_kernel<32><<<grid, 1024, smem, stream>>>(p);
+// dW += sum_fs dwp[fs][..][l < d],  dbias += sum_fs dwp[fs][..][d]
+__global__ void reduce_dwp_kernel(const BwdParams p) {
+  const int d1 = p.d + 1;
+  const long long n = (long long)p.I * p.O * p.D * d1;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int fs = 0; fs < p.FS; ++fs) s += p.dwp[(size_t)fs * n + e];
+    const long long row = e / d1;
+    const int l = (int)(e - row * d1);
+    if (l < p.d) p.dW[row * p.d + l] += s;
+    else p.dbias[row] += s;
+  }
 }
 
-// d_emb[b,s',h,l] += sum_w dxw[(b, s'+lpad-w), w*H+h, l]   (fold the window back)
-__global__ void fold_dx_kernel(const BwdParams p, int T) {
+cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_t stream) {
+  DwdxPlan pl;
+  if (!dwdx_plan(p, max_smem, &pl)) return cudaErrorInvalidValue;
+  int ftsh = 0;
+  while ((1 << ftsh) < pl.FT) ++ftsh;
+  dim3 grid(p.I, p.FS, p.OP / 32);
+  cudaError_t e;
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (ee != cudaSuccess) return ee;
+    kern<<<grid, pl.NT, pl.smem, stream>>>(p, pl.FT, ftsh, pl.NTc, pl.P);
+    return cudaSuccess;
+  };
+  if (pl.aug && pl.NT <= 512) e = go(dwdx_from_saved_kernel<true, 512>);
+  else if (pl.aug) e = go(dwdx_from_saved_kernel<true, 1024>);
+  else e = go(dwdx_from_saved_kernel<false, 1024>);
+  if (e != cudaSuccess) return e;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const long long n = (long long)p.I * p.O * p.D * (p.d + 1);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  reduce_dwp_kernel<<<blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// d_emb[b,s',h,l] += sum_w sum_q dxw[(b, s'+lpad-w), w*H+h, q, l]   (fold the window back)
+__global__ void fold_dx_kernel(const BwdParams p) {
   const long long n = (long long)p.B * p.S * p.H * p.d;
-  const int window = p.I / p.H;
+  const int window = p.I / p.H, OPL = p.OP / 32;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     const int l = (int)(e % p.d);
@@ -593,38 +887,59 @@ __global__ void fold_dx_kernel(const BwdParams p, int T) {
     float acc = 0.f;
     for (int w = 0; w < window; ++w) {
       const int sf = s + p.lpad - w;
-      if (sf >= 0 && sf < p.S)
-        acc += p.dxw[(((long long)b * p.S + sf) * p.I + w * p.H + hc) * T + l];
+      if (sf >= 0 && sf < p.S) {
+        const float* src = p.dxw + ((((long long)b * p.S + sf) * p.I + w * p.H + hc) * OPL) * p.dp + l;
+        for (int c = 0; c < OPL; ++c) acc += src[c * p.dp];
+      }
     }
     p.d_emb[e] += acc;
   }
 }
 
-void launch_fold_dx(const BwdParams& p, int T, cudaStream_t stream) {
+void launch_fold_dx(const BwdParams& p, cudaStream_t stream) {
   const long long n = (long long)p.B * p.S * p.H * p.d;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  fold_dx_kernel<<<blocks, 256, 0, stream>>>(p, T);
+  fold_dx_kernel<<<blocks, 256, 0, stream>>>(p);
 }
 
-template <int T, int OPL>
+template <int T, int OPL, int NW, int UM, bool SPLIT>
 static cudaError_t launch_bwd_variant(const BwdParams& p, int nchains, cudaStream_t stream) {
-  constexpr int NW = 8;
   const size_t E = (size_t)OPL * T * 32;
-  const size_t smem = sizeof(float) * ((size_t)p.I * T + NW * E + (2 * BW_MAX_ITERS + 1) * E + 3 * E);
-  auto kern = route_layer_bwd_kernel<T, OPL, NW>;
+  const size_t smem = sizeof(float) * ((UM == 0 ? (size_t)p.Ic * T : 0) + (NW + 2) * E +
+                                       (2 * BW_MAX_ITERS + 1) * E + 3 * E);
+  auto kern = route_layer_bwd_kernel<T, OPL, NW, UM, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<nchains, NW * 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nchains * p.C));
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-#define SRF_BWD(T_, OPL_) \
-  if (T == T_ && OPL == OPL_) return launch_bwd_variant<T_, OPL_>(p, nchains, stream);
+int route_layer_bwd_warps(int um) { return um == 1 ? SRF_BWD_NW_BF16 : (um == 2 ? SRF_BWD_NW_F32 : 8); }
 
-cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int nchains,
+#define SRF_BWD(T_, OPL_)                                                                      \
+  if (T == T_ && OPL == OPL_) {                                                                \
+    if (um == 1) return launch_bwd_variant<T_, OPL_, SRF_BWD_NW_BF16, 1, true>(p, nchains, stream); \
+    if (um == 2) return launch_bwd_variant<T_, OPL_, SRF_BWD_NW_F32, 2, true>(p, nchains, stream); \
+    if (p.split) return launch_bwd_variant<T_, OPL_, 8, 0, true>(p, nchains, stream);         \
+    return launch_bwd_variant<T_, OPL_, 8, 0, false>(p, nchains, stream);                     \
+  }
+
+cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int um, int nchains,
                                    cudaStream_t stream) {
   if (p.iters > BW_MAX_ITERS) return cudaErrorInvalidValue;
+  if (um != 0 && !p.split) return cudaErrorInvalidValue;
   SRF_BWD(8, 1)
   SRF_BWD(8, 2)
   SRF_BWD(8, 4)

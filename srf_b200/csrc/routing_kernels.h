@@ -67,12 +67,27 @@ struct BwdParams {
   float* gabuf;  // [frames][R][I][OP]
   float* gtT;    // [frames][R][O][T]
   float* vaT;    // [frames][R][O][T]
-  float* dxw;    // [frames][I][T]   dL/dx of the windowed input
+  float* dxw;    // [frames][I][OPL][dp]   dL/dx of the windowed input, per 32-capsule chunk
+  // phase B (dwdx_from_saved_kernel)
+  const float* W;  // canonical [I][O][D][d] weights
+  int Tu;          // row length of gtT / vaT (the BPTT kernel's T)
+  int dp;          // d rounded up to a multiple of 4 (row length of dxw)
+  int FS;          // frame splits of phase B; partial sums go to dwp
+  int fps;         // frames per split
+  float* dwp;      // [FS][I][O][D][d+1]   partial dW (l < d) and dbias (l == d)
+  // streamed u_hat (uhat_mode TF32 / BF16): the BPTT kernel reads the tcgen05 GEMM's output
+  const void* u;
+  int halfB;
+  // cluster split of the BPTT sweep: C CTAs per chain, Ic input capsules each
+  int C, Ic;
 };
-void launch_dw_from_saved(const BwdParams& p, int T, cudaStream_t stream);
-void launch_fold_dx(const BwdParams& p, int T, cudaStream_t stream);
+int route_layer_bwd_warps(int um);
+size_t dwdx_smem_bytes(int D, int d, int P, int FT);
+int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms);
+cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_t stream);
+void launch_fold_dx(const BwdParams& p, cudaStream_t stream);
 void launch_ln_head_bwd(const BwdParams& p, cudaStream_t stream);
-cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int nchains,
+cudaError_t launch_route_layer_bwd(const BwdParams& p, int T, int OPL, int um, int nchains,
                                    cudaStream_t stream);
 
 // CTC + Adam (ctc_adam.cu)

@@ -426,13 +426,22 @@ BWD_CASES = [
     (3, 3, 7, 4, 9, 12, 1, 1, 2, True, True),     # d != D
     (2, 3, 12, 20, 30, 20, 1, 1, 1, True, False),  # WSJ dims
     (1, 4, 6, 8, 40, 8, 0, 0, 2, False, True),     # 2 output capsules per lane
+    (4, 70, 4, 4, 5, 4, 1, 1, 1, True, False),     # 280 frames: several tiles and frame splits
+    (3, 90, 3, 4, 6, 8, 0, 1, 2, False, True),     # odd batch, DR, 270 frames
 ]
+# tolerance of (forward capsules, gradients) per u_hat mode; the tensor modes differentiate the
+# function they compute (rounded u_hat), so their gradients carry the same rounding class
+BWD_TOL = {"fp32": (1e-4, 2e-4), "tf32": (5e-3, 1e-2), "bf16": (2e-2, 4e-2)}
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("case", BWD_CASES)
-def test_layer_backward_matches_autograd(case):
+def test_layer_backward_matches_autograd(case, mode):
   from srf_b200 import routing
   B, S, H, d, O, D, lpad, rpad, iters, sdr, last = case
+  ftol, gtol = BWD_TOL[mode]
+  if mode != "fp32" and iters > 1:
+    ftol, gtol = 2 * ftol, 2 * gtol   # every routing pass re-uses the rounded u_hat
   g = torch.Generator().manual_seed(31)
   win = lpad + rpad + 1
   emb = torch.randn(B, S, H, d, generator=g, dtype=torch.float64)
@@ -457,9 +466,10 @@ def test_layer_backward_matches_autograd(case):
   f = lambda t: t.detach().float().cuda()
   args = routing.LayerArgs(W=f(W), bias=f(bias), lpad=lpad, rpad=rpad, iters=iters, sdr=sdr,
                            mask_class0=last, ln_gamma=f(gam), ln_beta=f(bet), dropout_mask=f(mask),
-                           head_gamma=f(hg) if last else None, head_beta=f(hb) if last else None)
+                           head_gamma=f(hg) if last else None, head_beta=f(hb) if last else None,
+                           uhat_mode=mode)
   caps, lg, raw = routing.route_layer_fwd_train(f(emb), args)
-  assert rel_err(raw, v.detach()) < 1e-4
+  assert rel_err(raw, v.detach()) < ftol
   got = routing.route_layer_bwd(f(emb), args, raw, d_out=None if last else f(wc),
                                 d_logits=f(wl) if last else None)
   torch.cuda.synchronize()
@@ -467,7 +477,7 @@ def test_layer_backward_matches_autograd(case):
   if last:
     checks += [("dhead_gamma", hg.grad), ("dhead_beta", hb.grad)]
   for name, ref in checks:
-    assert rel_err(got[name].reshape(ref.shape), ref) < 2e-4, name
+    assert rel_err(got[name].reshape(ref.shape), ref) < gtol, name
 
 
 def test_stack_ctc_train_step_grads_match_autograd():

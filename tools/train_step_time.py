@@ -9,7 +9,7 @@ w = bench.WORKLOADS[name]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else w["B"]
 S = int(sys.argv[3]) if len(sys.argv) > 3 else (w["T"] + 3) // 4
 stack = RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"], w["lpad"], w["rpad"],
-                     w["iters"], w["sdr"], seed=0, inn_dropout=0.1, uhat_mode="fp32")
+                     w["iters"], w["sdr"], seed=0, inn_dropout=0.1, uhat_mode=os.environ.get("SRF_UHAT", "bf16"))
 names = [n for n, _ in stack.named_parameters()]
 opt = training.FlatAdam([t for _, t in stack.named_parameters()])
 g = torch.Generator().manual_seed(1)
@@ -17,7 +17,7 @@ emb = torch.randn(B, S, w["PH"], w["DIM"], generator=g).cuda()
 L = max(1, S // 3)
 labels = torch.randint(1, w["class_n"] - 1, (B, L), generator=g).cuda()
 in_len, lab_len = torch.full((B,), S).cuda(), torch.full((B,), L).cuda()
-for it in range(2):
+for it in range(3):
   torch.cuda.synchronize(); t0 = time.perf_counter()
   loss, grads, _ = stack.ctc_train_step_grads(emb, labels, in_len, lab_len)
   torch.cuda.synchronize(); t1 = time.perf_counter()

@@ -418,9 +418,11 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();
         for (int e = tid; e < E; e += NT) {
-          float acc = 0.f;
-          for (int rk = 0; rk < C; ++rk) acc += cluster.map_shared_rank(tsum, rk)[par * E + e];
-          tr[r * E + e] = acc;
+          float v[8];  // all remote loads in flight before the sum
+#pragma unroll
+          for (int rk = 0; rk < 8; ++rk)
+            v[rk] = rk < C ? cluster.map_shared_rank(tsum, rk)[par * E + e] : 0.f;
+          tr[r * E + e] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
         }
         par ^= 1;
       }
@@ -607,9 +609,11 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();
         for (int e = tid; e < E; e += NT) {
-          float acc = gacc[e];
-          for (int rk = 0; rk < C; ++rk) acc += cluster.map_shared_rank(tsum, rk)[par * E + e];
-          gacc[e] = acc;
+          float v[8];
+#pragma unroll
+          for (int rk = 0; rk < 8; ++rk)
+            v[rk] = rk < C ? cluster.map_shared_rank(tsum, rk)[par * E + e] : 0.f;
+          gacc[e] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
         }
         par ^= 1;
       }
@@ -683,8 +687,8 @@ int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms) {
   return (int)FS;
 }
 
-template <bool AUG, int MAXT>
-__global__ void __launch_bounds__(MAXT) dwdx_from_saved_kernel(const BwdParams p, int FT, int ftsh,
+template <bool AUG, int MAXT, int MINB, int GB>
+__global__ void __launch_bounds__(MAXT, MINB) dwdx_from_saved_kernel(const BwdParams p, int FT, int ftsh,
                                                                 int NTc, int P) {
   extern __shared__ __align__(16) float sm[];
   const int D = p.D, d = p.d, dp = p.dp, R = p.iters, O = p.O, I = p.I, OP = p.OP, Tu = p.Tu;
@@ -708,7 +712,6 @@ __global__ void __launch_bounds__(MAXT) dwdx_from_saved_kernel(const BwdParams p
     if (j < nj && l < d) v = p.W[(((size_t)i * O + jbase + j) * D + k) * d + l];
     Ws[e] = v;
   }
-  const unsigned magicD = (65536u + D - 1) / D;  // e / D for e < 1056, D <= 32
   const int lw = AUG ? d1 : d;
   const bool dw_thread = tid < NTc;
   const int k_dw = tid / lw, l_dw = tid - k_dw * lw;
@@ -739,35 +742,58 @@ __global__ void __launch_bounds__(MAXT) dwdx_from_saved_kernel(const BwdParams p
       }
       xs[e] = v;
     }
-    // (b) g_u of the tile: each thread owns (j, k) elements and walks the frames eight at a time
-    // with all 32 loads of a group in flight
-    for (int e2 = tid; e2 < 32 * D; e2 += NT) {
-      const int j = (int)(((unsigned)e2 * magicD) >> 16), k = e2 - j * D;
-      const bool jok = j < nj;
-      for (int ft0 = 0; ft0 < FT; ft0 += 8) {
-        float g[8];
+    // (b) g_u of the tile: a work item is (group of GB frames, j, 4 consecutive k); g_t / Vacc
+    // rows are read with 16-byte loads, all loads of an item in flight together
+    {
+      const int D4 = (D + 3) >> 2, per = 32 * D4, NG = (FT + GB - 1) / GB;
+      const size_t cstride = (size_t)R * I * OP, gstride = (size_t)R * O * Tu;
+      for (int it = tid; it < NG * per; it += NT) {
+        const int grp = it / per, rem = it - grp * per;
+        const int j = rem / D4, k4 = rem - j * D4;
+        const bool jok = j < nj;
+        const int jc = jok ? j : 0;
+        const int ft0 = grp * GB;
+        const float* cb = p.cbuf + ((size_t)f0 * R * I + i) * OP + jbase + jc;
+        const float* gab = p.gabuf + ((size_t)f0 * R * I + i) * OP + jbase + jc;
+        const float* gtb = p.gtT + ((size_t)f0 * R * O + jbase + jc) * Tu + k4 * 4;
+        const float* vab = p.vaT + ((size_t)f0 * R * O + jbase + jc) * Tu + k4 * 4;
+        float4 g[GB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) g[u] = 0.f;
+        for (int u = 0; u < GB; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < R; ++r) {
-          float cv[8], gav[8], gtv[8], vav[8];
+          float cv[GB], gav[GB];
+          float4 gtv[GB], vav[GB];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int ft = ft0 + u;
-            const bool ok = jok && ft < nf;
-            const size_t fr = (size_t)(f0 + (ok ? ft : 0)) * R + r;
-            const size_t co = (fr * I + i) * OP + jbase + (ok ? j : 0);
-            const size_t go = (fr * O + jbase + (ok ? j : 0)) * Tu + k;
-            cv[u] = ok ? __ldg(p.cbuf + co) : 0.f;
-            gav[u] = ok ? __ldg(p.gabuf + co) : 0.f;
-            gtv[u] = ok ? __ldg(p.gtT + go) : 0.f;
-            vav[u] = ok ? __ldg(p.vaT + go) : 0.f;
+          for (int u = 0; u < GB; ++u) {
+            // frames past the end of the tile re-read the last valid one (zeroed at the store)
+            const int ft = (ft0 + u) < nf ? (ft0 + u) : (nf - 1);
+            const size_t oc = ft * cstride + (size_t)r * I * OP;
+            const size_t og = ft * gstride + (size_t)r * O * Tu;
+            cv[u] = __ldg(cb + oc);
+            gav[u] = __ldg(gab + oc);
+            gtv[u] = __ldg(reinterpret_cast<const float4*>(gtb + og));
+            vav[u] = __ldg(reinterpret_cast<const float4*>(vab + og));
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) g[u] = fmaf(cv[u], gtv[u], fmaf(gav[u], vav[u], g[u]));
+          for (int u = 0; u < GB; ++u) {
+            g[u].x = fmaf(cv[u], gtv[u].x, fmaf(gav[u], vav[u].x, g[u].x));
+            g[u].y = fmaf(cv[u], gtv[u].y, fmaf(gav[u], vav[u].y, g[u].y));
+            g[u].z = fmaf(cv[u], gtv[u].z, fmaf(gav[u], vav[u].z, g[u].z));
+            g[u].w = fmaf(cv[u], gtv[u].w, fmaf(gav[u], vav[u].w, g[u].w));
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (ft0 + u < FT) gus[(ft0 + u) * GS + k * 36 + j] = g[u];
+        for (int u = 0; u < GB; ++u) {
+          const int ft = ft0 + u;
+          if (ft < FT) {
+            const bool ok = jok && ft < nf;
+            float* dst = gus + ft * GS + (k4 * 4) * 36 + j;
+            const float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (k4 * 4 + c < D) dst[c * 36] = ok ? gv[c] : 0.f;
+          }
+        }
       }
     }
     __syncthreads();
@@ -796,14 +822,16 @@ __global__ void __launch_bounds__(MAXT) dwdx_from_saved_kernel(const BwdParams p
     if (dx_thread) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* grow = gus + ft_dx * GS;
+      const float* wbase = Ws + lq * 4;
+      const int wj = D * dp;  // floats per output capsule in Ws
       for (int un = part; un < 8 * D; un += P) {
         const int k = un >> 3, j4 = un & 7;
         const float4 g4 = *reinterpret_cast<const float4*>(grow + k * 36 + j4 * 4);
         const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float* wp = wbase + j4 * 4 * wj + k * dp;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const float4 w4 =
-              *reinterpret_cast<const float4*>(Ws + ((size_t)(j4 * 4 + jj) * D + k) * dp + lq * 4);
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + jj * wj);
           a.x = fmaf(gv[jj], w4.x, a.x);
           a.y = fmaf(gv[jj], w4.y, a.y);
           a.z = fmaf(gv[jj], w4.z, a.z);
@@ -859,9 +887,9 @@ cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_
     kern<<<grid, pl.NT, pl.smem, stream>>>(p, pl.FT, ftsh, pl.NTc, pl.P);
     return cudaSuccess;
   };
-  if (pl.aug && pl.NT <= 512) e = go(dwdx_from_saved_kernel<true, 512>);
-  else if (pl.aug) e = go(dwdx_from_saved_kernel<true, 1024>);
-  else e = go(dwdx_from_saved_kernel<false, 1024>);
+  if (pl.aug && pl.NT <= 512) e = go(dwdx_from_saved_kernel<true, 512, 1, 4>);
+  else if (pl.aug) e = go(dwdx_from_saved_kernel<true, 1024, 1, 4>);
+  else e = go(dwdx_from_saved_kernel<false, 1024, 1, 4>);
   if (e != cudaSuccess) return e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -51,11 +51,22 @@ constexpr int BW_MAX_ITERS = 8;
 // K_b1: head + dropout + LayerNorm backward.  grid = frames / 8, block = 256 (warp per frame)
 // ---------------------------------------------------------------------------------------
 __global__ void ln_head_bwd_kernel(const BwdParams p) {
+  extern __shared__ float lsm[];
   const int lane = threadIdx.x & 31;
-  const long long frame = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (frame >= (long long)p.B * p.S) return;
   const int O = p.O, D = p.D;
   const int n = O * D;
+  // parameter gradients are summed per CTA in shared memory over its strip of frames and leave
+  // with one global atomic per element and CTA
+  float* sg = lsm;          // [n] dgamma
+  float* sb = sg + n;       // [n] dbeta
+  float* shg = sb + n;      // [O] dhead_gamma
+  float* shb = shg + O;     // [O] dhead_beta
+  for (int e = threadIdx.x; e < 2 * n + 2 * O; e += blockDim.x) lsm[e] = 0.f;
+  __syncthreads();
+  const long long frames = (long long)p.B * p.S;
+  const int wpb = blockDim.x >> 5;
+  for (long long frame = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); frame < frames;
+       frame += (long long)gridDim.x * wpb) {
   const float* v = p.v_raw + frame * n;
   const bool do_ln = p.ln_gamma != nullptr;
   // pass 1: LayerNorm statistics of v_raw
@@ -115,8 +126,8 @@ __global__ void ln_head_bwd_kernel(const BwdParams p) {
       }
       const float zhat = (sqrtf(l2 + p.length_eps) - hm) * hr;
       const float dl = p.d_logits[frame * O + j];
-      atomicAdd(p.dhead_gamma + j, dl * zhat);
-      atomicAdd(p.dhead_beta + j, dl);
+      atomicAdd(shg + j, dl * zhat);
+      atomicAdd(shb + j, dl);
       const float dz = dl * p.head_gamma[j];
       a += dz;
       b = fmaf(dz, zhat, b);
@@ -153,8 +164,8 @@ __global__ void ln_head_bwd_kernel(const BwdParams p) {
       float g = dy_of(j, k, y, len_j, zhat_j);
       if (p.dropout_mask) g *= p.dropout_mask[frame * n + e];
       if (do_ln) {
-        atomicAdd(p.dgamma + e, g * xhat);
-        atomicAdd(p.dbeta + e, g);
+        atomicAdd(sg + e, g * xhat);
+        atomicAdd(sb + e, g);
         const float dxh = g * p.ln_gamma[e];
         m1 += dxh;
         m2 = fmaf(dxh, xhat, m2);
@@ -163,7 +174,7 @@ __global__ void ln_head_bwd_kernel(const BwdParams p) {
       }
     }
   }
-  if (!do_ln) return;
+  if (!do_ln) continue;
   m1 = bw_sum(m1) / (float)n;
   m2 = bw_sum(m2) / (float)n;
   for (int j = lane; j < O; j += 32) {
@@ -187,12 +198,27 @@ __global__ void ln_head_bwd_kernel(const BwdParams p) {
       p.d_raw[frame * n + e] = rstd * (dxh - m1 - xhat * m2);
     }
   }
+  }  // frames of this warp
+  __syncthreads();
+  if (p.ln_gamma != nullptr)
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      atomicAdd(p.dgamma + e, sg[e]);
+      atomicAdd(p.dbeta + e, sb[e]);
+    }
+  if (p.d_logits != nullptr)
+    for (int j = threadIdx.x; j < O; j += blockDim.x) {
+      atomicAdd(p.dhead_gamma + j, shg[j]);
+      atomicAdd(p.dhead_beta + j, shb[j]);
+    }
 }
 
 void launch_ln_head_bwd(const BwdParams& p, cudaStream_t stream) {
   const long long frames = (long long)p.B * p.S;
   const int warps = 8;
-  ln_head_bwd_kernel<<<(unsigned)((frames + warps - 1) / warps), warps * 32, 0, stream>>>(p);
+  long long blocks = (frames + warps - 1) / warps;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  const size_t smem = sizeof(float) * (2 * (size_t)p.O * p.D + 2 * (size_t)p.O);
+  ln_head_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -241,6 +267,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
   int par = 0;
   // dL/dv_raw of a frame and the carried output of the frame before it, fetched one step ahead
   float nd[PER], nv[PER];
+  uint4 raw0[RAWN];
   auto fetch_frame = [&](int step_) {
     const int b_ = p.sdr ? chain : chain / p.S;
     const int sf_ = p.sdr ? step_ : chain % p.S;
@@ -265,15 +292,15 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
     const long long gg = (long long)sf * p.halfB + (b >> 1);
     const bool mem1 = (b & 1) != 0;
     const size_t ustride_i = (size_t)OPL * T4 * 128 * 2;  // elements per (pair, i)
-    auto load_raw = [&](int i, uint4(&dst)[RAWN]) {
+    auto load_raw_at = [&](long long gq, int i, uint4(&dst)[RAWN]) {
       if (UM == 1) {
         const uint4* src = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const uint16_t*>(p.u) + ((size_t)gg * I + i) * ustride_i);
+            reinterpret_cast<const uint16_t*>(p.u) + ((size_t)gq * I + i) * ustride_i);
 #pragma unroll
         for (int m = 0; m < OPL * T4; ++m) dst[m] = __ldg(src + m * 32 + lane);
       } else if (UM == 2) {
         const uint4* src = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const float*>(p.u) + ((size_t)gg * I + i) * ustride_i);
+            reinterpret_cast<const float*>(p.u) + ((size_t)gq * I + i) * ustride_i);
 #pragma unroll
         for (int m = 0; m < OPL * T4; ++m) {
           dst[(2 * m) % RAWN] = __ldg(src + (m * 32 + lane) * 2);
@@ -281,6 +308,10 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         }
       }
     };
+    auto load_raw = [&](int i, uint4(&dst)[RAWN]) { load_raw_at(gg, i, dst); };
+    // raw0 = this warp's first capsule of the frame: loaded once (during the previous step),
+    // used by every pass of the frame
+    if (UM != 0 && step == p.nsteps - 1 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw0);
     // element (k_in, member) of chunk m = (q, k4) sits at 2*k_in + member
     auto unpack = [&](const uint4(&raw)[RAWN], float(&u)[OPL][T]) {
 #pragma unroll
@@ -341,6 +372,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
       const int e = tid + u * NT;
       if (e < E) {
         gout[e] = nd[u] + (p.sdr ? gacc[e] : 0.f);
+        gacc[e] = 0.f;  // G_R = 0 for the backward passes of this frame
         vacc[e] = nv[u];
       }
     }
@@ -369,7 +401,8 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           ta[q][k] = 0.f;
         }
       uint4 raw[RAWN];
-      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
+#pragma unroll
+      for (int m = 0; m < RAWN; ++m) raw[m] = raw0[m];
       for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[OPL][T], a[OPL];
         if (UM != 0) {
@@ -446,8 +479,6 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
     }
 
     // ---------------- backward over the passes ----------------
-    for (int e = tid; e < E; e += NT) gacc[e] = 0.f;  // G_R = 0
-    __syncthreads();
     for (int r = R - 1; r >= 0; --r) {
       // g_v = [last] g_out + G_{r+1};  g_t = squash'(t_r) g_v
       for (int idx = tid; idx < OPL * 32; idx += NT) {
@@ -495,7 +526,8 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           gv_acc[q][k] = 0.f;
         }
       uint4 raw[RAWN];
-      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
+#pragma unroll
+      for (int m = 0; m < RAWN; ++m) raw[m] = raw0[m];
       for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[OPL][T], a[OPL];
         if (UM != 0) {
@@ -592,6 +624,8 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           }
         }
       }
+      if (UM != 0 && r == 0 && step > 0 && i_lo + warp < i_hi)
+        load_raw_at((long long)(sf - 1) * p.halfB + (b >> 1), i_lo + warp, raw0);
       // G_r = G_{r+1} + sum_i g_a u
 #pragma unroll
       for (int q = 0; q < OPL; ++q)

@@ -111,8 +111,9 @@ int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, int32_t n_l
  * tf.GradientTape through the tf.while_loop, tfsr/trainer_sr.py:62-71).  `layer` is the SAME
  * descriptor the forward call used (emb, W, bias, LayerNorm/head parameters, dropout mask,
  * knobs; its out_* pointers are ignored).  All gradient outputs ACCUMULATE (+=): zero them
- * before the first call.  u_hat is recomputed in FP32 inside the kernel (nothing but the
- * layer input and `v_raw` is saved by the forward pass).
+ * before the first call.  Nothing but the layer input and `v_raw` is saved by the forward pass:
+ * u_hat is recomputed -- in FP32 from the weights with uhat_mode FP32, by the tcgen05 GEMM
+ * (streamed by the sweep, same rounding as the forward) with uhat_mode TF32 / BF16.
  *   v_raw        [B,S,O,D]  forward's out_raw of this layer
  *   d_out        [B,S,O,D]  dL/d(out_caps) from the next layer's d_emb; NULL on the last layer
  *   d_logits     [B,S,O]    dL/d(out_logits); NULL unless the layer carries the head

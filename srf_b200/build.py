@@ -19,8 +19,9 @@ SOURCES = ["capi.cu", "routing_fwd.cu", "uhat_gemm.cu", "routing_stream.cu", "ro
 HEADERS = ["routing_kernels.h", "sm100_ptx.cuh", os.path.join("..", "..", "include", "srf_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJDIR = os.path.join(HERE, "_build")
 
 
 def _nvcc() -> str:
@@ -45,13 +46,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(STAMP) as f:
       if f.read().strip() == digest:
         return LIB
-  cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-  res = subprocess.run(cmd, capture_output=True, text=True)
+  # one nvcc process per translation unit, in parallel, then one link
+  from concurrent.futures import ThreadPoolExecutor
+  os.makedirs(OBJDIR, exist_ok=True)
+  extra = ["-Xptxas", "-v"] if verbose else []
+
+  def compile_one(src):
+    obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
+    return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+  with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+    results = list(pool.map(compile_one, SOURCES))
+  for src, _, res in results:
+    if verbose or res.returncode != 0:
+      sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+      raise RuntimeError("nvcc failed compiling %s (exit %d)" % (src, res.returncode))
+  res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] +
+                       [obj for _, obj, _ in results], capture_output=True, text=True)
   if verbose or res.returncode != 0:
     sys.stderr.write(res.stdout + res.stderr)
   if res.returncode != 0:
-    raise RuntimeError("nvcc failed building libsrf_b200.so (exit %d)" % res.returncode)
+    raise RuntimeError("nvcc failed linking libsrf_b200.so (exit %d)" % res.returncode)
   with open(STAMP, "w") as f:
     f.write(digest)
   return LIB

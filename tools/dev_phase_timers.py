@@ -8,6 +8,8 @@ import bench
 from srf_b200 import RoutingStack
 w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else 'cfg3']
 B, S = w['B'], (w['T'] + 3) // 4
+if len(sys.argv) > 2:
+  B = int(sys.argv[2])
 stack = RoutingStack(w['L'], w['PH'], w['CH'], w['class_n'], w['DIM'], w['DIM'], w['DIM'], w['lpad'], w['rpad'],
                      w['iters'], w['sdr'], seed=0, uhat_mode='bf16')
 emb = torch.randn(B, S, w['PH'], w['DIM'], device='cuda')

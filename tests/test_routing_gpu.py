@@ -562,3 +562,22 @@ def test_host_pipeline_matches_direct_forward():
     assert torch.equal(a, r)
   with pytest.raises(RuntimeError):
     pipe.result()
+
+
+def test_checkpoint_round_trip_and_average_on_the_stack(tmp_path):
+  """a stack restored from a checkpoint (stored in the naive variant's
+  variable layout) gives identical logits; the average of two checkpoints is the mean."""
+  from srf_b200 import RoutingStack, checkpoint as ck
+  mk = lambda seed: RoutingStack(3, 12, 6, 9, 8, 8, 8, 1, 1, 1, True, seed=seed)
+  a, b, c = mk(1), mk(2), mk(3)
+  emb = torch.randn(2, 9, 12, 8, generator=torch.Generator().manual_seed(0)).cuda()
+  ck.save_checkpoint(ck.state_dict(a), str(tmp_path), 1, variant="naive")
+  ck.save_checkpoint(ck.state_dict(b), str(tmp_path), 2, variant="einsum")
+  assert not torch.equal(c.forward(emb), a.forward(emb))
+  assert ck.load_checkpoint(c, str(tmp_path), path_ckpt_epoch=1, strict=True) == 1
+  assert torch.equal(c.forward(emb), a.forward(emb))
+  assert ck.load_checkpoint(c, str(tmp_path), strict=True) == 2
+  assert torch.equal(c.forward(emb), b.forward(emb))
+  ck.load_state_dict(c, ck.read_checkpoint(ck.average_checkpoints(str(tmp_path), 2)))
+  for (n, t), (_, ta), (_, tb) in zip(c.named_parameters(), a.named_parameters(), b.named_parameters()):
+    assert torch.allclose(t, (ta + tb) / 2, atol=1e-7), n

@@ -826,7 +826,7 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   const long long nchains = L->sdr ? L->B : (long long)L->B * L->S;
   {
     // cluster split over the input capsules when there are fewer chains than SMs (SDR)
-    const int nw = srf::route_layer_bwd_warps(um);
+    const int nw = srf::route_layer_bwd_warps(um, T, OPL);
     int C = pow2_floor(h->num_sms / nchains > 0 ? (int)(h->num_sms / nchains) : 1);
     if (C > 8) C = 8;
     while (C > 1 && (I + C - 1) / C < nw / 2) C /= 2;
@@ -834,6 +834,8 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
     if (!p.split) C = 1;
     p.C = C;
     p.Ic = (I + C - 1) / C;
+    p.dbg = h->dbg;
+    p.l2_prefetch = getenv("SRF_BWD_NOPF") ? 0 : 1;
   }
   {
     KernelSpan span(h, 2, stream);

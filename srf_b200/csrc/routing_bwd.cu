@@ -25,13 +25,30 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cuda.h>
+
 #include "routing_kernels.h"
+#include "sm100_ptx.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace srf {
 
 namespace {
+__device__ __forceinline__ uint32_t bw_map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// remote store of 4 floats into a peer CTA's shared memory that completes (by byte count) on that
+// peer's mbarrier: data and signal in one instruction (the exchange of routing_stream.cu)
+__device__ __forceinline__ void bw_st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+          remote_addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
+      : "memory");
+}
 __device__ __forceinline__ float bw_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -42,8 +59,24 @@ __device__ __forceinline__ float bw_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// tensor modes: both softmax reductions as single REDUX instructions (the max on an
+// order-preserving integer image of the floats, the sum on an unsigned Q26 image of exp(a - max)
+// in (0, 1]; same construction as routing_stream.cu)
+__device__ __forceinline__ float bw_max_redux(float v) {
+  int mi = __float_as_int(v);
+  mi ^= (mi >> 31) & 0x7fffffff;
+  mi = __reduce_max_sync(0xffffffffu, mi);
+  mi ^= (mi >> 31) & 0x7fffffff;
+  return __int_as_float(mi);
+}
+template <int OPL>
+__device__ __forceinline__ float bw_sum_redux(float z) {
+  constexpr float QS = (float)(1 << 26) / (float)OPL;
+  const unsigned zi = __reduce_add_sync(0xffffffffu, __float2uint_rn(z * QS));
+  return (float)zi * (1.0f / QS);
+}
 constexpr int BW_MAX_ITERS = 8;
-#define SRF_BWD_NW_BF16 16
+#define SRF_BWD_NW_BF16 12
 #define SRF_BWD_NW_F32 12
 }  // namespace
 
@@ -250,24 +283,93 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
   const int i_lo = rank * p.Ic;
   const int i_hi = min(I, i_lo + p.Ic);
   constexpr int PER = (E + NT - 1) / NT;
-  float* xs = smem;                 // [Ic][T] window-gathered input of the frame (UM == 0)
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem);  // [2] exchange barriers (16 bytes)
+  float* xs = smem + 4;             // [Ic][T] window-gathered input of the frame (UM == 0)
   float* red = xs + (UM == 0 ? (size_t)p.Ic * T : 0);  // [NW][E]
-  float* tsum = red + NW * E;       // [2][E]   CTA partial for the cluster exchange
-  float* tr = tsum + 2 * E;         // [R][E]   t_r
+  float* xbuf = red + NW * E;       // [2][C][E] CTA partials of the cluster exchange (own + pushed)
+  float* tr = xbuf + (size_t)2 * C * E;  // [R][E]   t_r
   float* vacc = tr + BW_MAX_ITERS * E;  // [R+1][E] Vacc_0 .. Vacc_R
   float* gout = vacc + (BW_MAX_ITERS + 1) * E;  // [E] dL/dv of this frame (incl. BPTT carry)
   float* gt = gout + E;             // [E] g_t of the current pass
   float* gacc = gt + E;             // [E] G_r
+  float* ndb = gacc + E;            // [E] next frame's dL/dv_raw (cp.async landing zone)
+  float* nvb = ndb + E;             // [E] next frame's carried output
 
   const float4* __restrict__ Wp = reinterpret_cast<const float4*>(p.Wp);
   const float* __restrict__ Bp = p.Bp;
 
   for (int e = tid; e < E; e += NT) gacc[e] = 0.f;  // BPTT carry into the last frame is zero
+  if (tid == 0) {
+    ptx::mbar_init(&xfull[0], 1 + NW);  // expect_tx arrive + one arrive per warp (own copy stored)
+    ptx::mbar_init(&xfull[1], 1 + NW);
+    ptx::fence_barrier_init();
+  }
   __syncthreads();
+  if (C > 1) cg::this_cluster().sync();  // peers' barriers are initialised before anybody pushes
   int par = 0;
-  // dL/dv_raw of a frame and the carried output of the frame before it, fetched one step ahead
-  float nd[PER], nv[PER];
-  uint4 raw0[RAWN];
+  uint32_t nexch = 0;
+  // Sum the per-warp partials in `red` over the warps and over the cluster's CTAs.  Every CTA
+  // pushes its partial into every peer's xbuf[par][rank] with st.async (completes on the peer's
+  // mbarrier: no cluster barrier, no remote loads) and sums the C partials in rank order, so all
+  // CTAs hold bit-identical totals.  Call after a __syncthreads(); `sink(e4, total)` stores.
+  auto exchange = [&](auto sink) {
+    const float4* red4 = reinterpret_cast<const float4*>(red);
+    if (C > 1) {
+      uint64_t* xf = &xfull[par];
+      if (tid == 0) ptx::mbar_arrive_expect_tx(xf, (uint32_t)(C - 1) * E * 4);
+      float* mine = xbuf + ((size_t)par * C + rank) * E;
+      const uint32_t mine_a = ptx::smem_u32(mine), bar_a = ptx::smem_u32(xf);
+      for (int e4 = tid; e4 < E / 4; e4 += NT) {
+        float4 acc = red4[e4];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+          const float4 x = red4[(size_t)w * (E / 4) + e4];
+          acc.x += x.x;
+          acc.y += x.y;
+          acc.z += x.z;
+          acc.w += x.w;
+        }
+        reinterpret_cast<float4*>(mine)[e4] = acc;
+        for (int r2 = 1; r2 < C; ++r2) {
+          const int peer = (rank + r2) & (C - 1);  // C is a power of two
+          bw_st_async_v4(bw_map_to_rank(mine_a + e4 * 16, peer), acc, bw_map_to_rank(bar_a, peer));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(xf);
+      ptx::mbar_wait(xf, (nexch >> 1) & 1);
+      ++nexch;
+      const float4* xb4 = reinterpret_cast<const float4*>(xbuf + (size_t)par * C * E);
+      for (int e4 = tid; e4 < E / 4; e4 += NT) {
+        float4 acc = xb4[e4];
+        for (int r2 = 1; r2 < C; ++r2) {
+          const float4 x = xb4[(size_t)r2 * (E / 4) + e4];
+          acc.x += x.x;
+          acc.y += x.y;
+          acc.z += x.z;
+          acc.w += x.w;
+        }
+        sink(e4, acc);
+      }
+      par ^= 1;
+    } else {
+      for (int e4 = tid; e4 < E / 4; e4 += NT) {
+        float4 acc = red4[e4];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+          const float4 x = red4[(size_t)w * (E / 4) + e4];
+          acc.x += x.x;
+          acc.y += x.y;
+          acc.z += x.z;
+          acc.w += x.w;
+        }
+        sink(e4, acc);
+      }
+    }
+  };
+  // dL/dv_raw of a frame and the carried output of the frame before it are fetched one step
+  // ahead with cp.async into shared memory (no registers held across the frame; every thread
+  // fetches exactly the elements it consumes itself, so a per-thread wait is enough)
   auto fetch_frame = [&](int step_) {
     const int b_ = p.sdr ? chain : chain / p.S;
     const int sf_ = p.sdr ? step_ : chain % p.S;
@@ -275,19 +377,37 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
       const int e = tid + u * NT;
-      const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
-      const int j = q * 32 + ln;
-      const bool ok = e < E && j < O && k < D;
-      nd[u] = ok ? __ldg(p.d_raw + (fr_ * O + j) * D + k) : 0.f;
-      nv[u] = (ok && p.sdr && sf_ > 0) ? __ldg(p.v_raw + ((fr_ - 1) * O + j) * D + k) : 0.f;
+      if (e < E) {
+        const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
+        const int j = q * 32 + ln;
+        const bool ok = j < O && k < D;
+        const bool okv = ok && p.sdr && sf_ > 0;
+        const float* sd = p.d_raw + (ok ? (fr_ * O + j) * D + k : 0);
+        const float* sv = p.v_raw + (okv ? ((fr_ - 1) * O + j) * D + k : 0);
+        // src-size 0 zero-fills the destination
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ptx::smem_u32(ndb + e)), "l"(sd),
+                     "r"(ok ? 4 : 0));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ptx::smem_u32(nvb + e)), "l"(sv),
+                     "r"(okv ? 4 : 0));
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   fetch_frame(p.nsteps - 1);
 
+  // phase timers cost 18 live registers: compiled in only with -DSRF_BWD_PHASE_TIMERS
+#ifdef SRF_BWD_PHASE_TIMERS
+  const bool timing = p.dbg != nullptr && tid == 0;
+  long long tk[9];
+#define SRF_TK(n) if (timing) tk[n] = clock64();
+#else
+#define SRF_TK(n)
+#endif
   for (int step = p.nsteps - 1; step >= 0; --step) {
     const int b = p.sdr ? chain : chain / p.S;
     const int sf = p.sdr ? step : chain % p.S;
     const long long frame = (long long)b * p.S + sf;
+    SRF_TK(0)
     // streamed u_hat: frame pair index and which member of the pair this chain is
     const long long gg = (long long)sf * p.halfB + (b >> 1);
     const bool mem1 = (b & 1) != 0;
@@ -309,9 +429,6 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
       }
     };
     auto load_raw = [&](int i, uint4(&dst)[RAWN]) { load_raw_at(gg, i, dst); };
-    // raw0 = this warp's first capsule of the frame: loaded once (during the previous step),
-    // used by every pass of the frame
-    if (UM != 0 && step == p.nsteps - 1 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw0);
     // element (k_in, member) of chunk m = (q, k4) sits at 2*k_in + member
     auto unpack = [&](const uint4(&raw)[RAWN], float(&u)[OPL][T]) {
 #pragma unroll
@@ -367,19 +484,20 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
       xs[idx] = v;
     }
     // g_out = dL/d v_raw[frame] + carry; Vacc_0 = previous frame's output (SDR) or 0
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
       const int e = tid + u * NT;
       if (e < E) {
-        gout[e] = nd[u] + (p.sdr ? gacc[e] : 0.f);
+        gout[e] = ndb[e] + (p.sdr ? gacc[e] : 0.f);
         gacc[e] = 0.f;  // G_R = 0 for the backward passes of this frame
-        vacc[e] = nv[u];
+        vacc[e] = nvb[e];
       }
     }
     __syncthreads();
     if (step > 0) fetch_frame(step - 1);
     // pull the next step's u_hat lines of this warp's capsules into L2 while this step computes
-    if (UM != 0 && step > 0) {
+    if (UM != 0 && step > 0 && p.l2_prefetch) {
       constexpr int LINES = (int)(OPL * T4 * 128 * 2 * (UM == 1 ? 2 : 4) / 128);
       const long long ggn = (long long)(sf - 1) * p.halfB + (b >> 1);
       for (int i = i_lo + warp; i < i_hi; i += NW) {
@@ -390,6 +508,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
       }
     }
 
+    SRF_TK(1)
     // ---------------- forward recompute: t_r, Vacc_r ----------------
     for (int r = 0; r < R; ++r) {
       float va[OPL][T], ta[OPL][T];
@@ -401,8 +520,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           ta[q][k] = 0.f;
         }
       uint4 raw[RAWN];
-#pragma unroll
-      for (int m = 0; m < RAWN; ++m) raw[m] = raw0[m];
+      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
       for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[OPL][T], a[OPL];
         if (UM != 0) {
@@ -422,112 +540,98 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         float m = a[0];
 #pragma unroll
         for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[q]);
-        m = bw_max(m);
+        m = UM != 0 ? bw_max_redux(m) : bw_max(m);
         float ex[OPL], z = 0.f;
 #pragma unroll
         for (int q = 0; q < OPL; ++q) {
           ex[q] = exp2f((a[q] - m) * LOG2E);
           z += ex[q];
         }
-        const float inv = 1.0f / bw_sum(z);
+        const float inv = 1.0f / (UM != 0 ? bw_sum_redux<OPL>(z) : bw_sum(z));
 #pragma unroll
         for (int q = 0; q < OPL; ++q)
 #pragma unroll
           for (int k = 0; k < T; ++k) ta[q][k] = fmaf(ex[q] * inv, u[q][k], ta[q][k]);
       }
+      SRF_TK(2)
 #pragma unroll
       for (int q = 0; q < OPL; ++q)
 #pragma unroll
         for (int k = 0; k < T; ++k) red[warp * E + (q * T + k) * 32 + lane] = ta[q][k];
       __syncthreads();
-      for (int e = tid; e < E; e += NT) {
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) acc += red[w * E + e];
-        if (C > 1) tsum[par * E + e] = acc;
-        else tr[r * E + e] = acc;
-      }
-      if (C > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cluster.sync();
-        for (int e = tid; e < E; e += NT) {
-          float v[8];  // all remote loads in flight before the sum
-#pragma unroll
-          for (int rk = 0; rk < 8; ++rk)
-            v[rk] = rk < C ? cluster.map_shared_rank(tsum, rk)[par * E + e] : 0.f;
-          tr[r * E + e] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-        }
-        par ^= 1;
-      }
+      exchange([&](int e4, float4 tot) { reinterpret_cast<float4*>(tr + r * E)[e4] = tot; });
       __syncthreads();
-      for (int idx = tid; idx < OPL * 32; idx += NT) {
-        const int ln = idx & 31, q = idx >> 5;
-        float n2 = 0.f;
+      SRF_TK(3)
+      // Vacc_{r+1} is only needed by a later pass (the backward of pass r uses Vacc_r and t_r)
+      if (r + 1 < R) {
+        for (int idx = tid; idx < OPL * 32; idx += NT) {
+          const int ln = idx & 31, q = idx >> 5;
+          float n2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < T; ++k) {
-          const float t = tr[r * E + (q * T + k) * 32 + ln];
-          n2 = fmaf(t, t, n2);
-        }
-        const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
+          for (int k = 0; k < T; ++k) {
+            const float t = tr[r * E + (q * T + k) * 32 + ln];
+            n2 = fmaf(t, t, n2);
+          }
+          const float scale = (n2 / (1.0f + n2)) / sqrtf(n2 + 1e-7f);
 #pragma unroll
-        for (int k = 0; k < T; ++k) {
-          const int e = (q * T + k) * 32 + ln;
-          vacc[(r + 1) * E + e] = vacc[r * E + e] + tr[r * E + e] * scale;
+          for (int k = 0; k < T; ++k) {
+            const int e = (q * T + k) * 32 + ln;
+            vacc[(r + 1) * E + e] = vacc[r * E + e] + tr[r * E + e] * scale;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
 
+    SRF_TK(4)
     // ---------------- backward over the passes ----------------
     for (int r = R - 1; r >= 0; --r) {
-      // g_v = [last] g_out + G_{r+1};  g_t = squash'(t_r) g_v
-      for (int idx = tid; idx < OPL * 32; idx += NT) {
-        const int ln = idx & 31, q = idx >> 5;
+      // g_v = [last] g_out + G_{r+1};  g_t = squash'(t_r) g_v -- every warp for its own lanes,
+      // straight into registers (no serial phase, no barrier); rank 0 / warp 0 saves g_t, Vacc_r
+      SRF_TK(5)
+      float va[OPL][T], gtr[OPL][T], gv_acc[OPL][T];
+#pragma unroll
+      for (int q = 0; q < OPL; ++q) {
+        float tt[T], gv[T];
         float n2 = 0.f, dot = 0.f;
 #pragma unroll
         for (int k = 0; k < T; ++k) {
-          const int e = (q * T + k) * 32 + ln;
-          const float t = tr[r * E + e];
-          const float gv = (r == R - 1 ? gout[e] : 0.f) + gacc[e];
-          n2 = fmaf(t, t, n2);
-          dot = fmaf(gv, t, dot);
+          const int e = (q * T + k) * 32 + lane;
+          tt[k] = tr[r * E + e];
+          gv[k] = (r == R - 1 ? gout[e] : 0.f) + gacc[e];
+          va[q][k] = vacc[r * E + e];
+          gv_acc[q][k] = 0.f;
+          n2 = fmaf(tt[k], tt[k], n2);
+          dot = fmaf(gv[k], tt[k], dot);
         }
-        const float sq = sqrtf(n2 + 1e-7f);
-        const float f = n2 / ((1.0f + n2) * sq);
-        // f'(n2) = 1/((1+n2) sq) - f/(1+n2) - f/(2 (n2+eps))
-        const float fp = 1.0f / ((1.0f + n2) * sq) - f / (1.0f + n2) - 0.5f * f / (n2 + 1e-7f);
+        // f = n2 / ((1+n2) sqrt(n2+eps));  f'(n2) = 1/((1+n2) sq) - f/(1+n2) - f/(2 (n2+eps))
+        float f, fp;
+        if (UM != 0) {  // approximate rsqrt / rcp: the tensor modes' tolerance class
+          const float rsq = rsqrtf(n2 + 1e-7f), r1 = __frcp_rn(1.0f + n2);
+          f = n2 * r1 * rsq;
+          fp = r1 * rsq - f * r1 - 0.5f * f * rsq * rsq;
+        } else {
+          const float sq = sqrtf(n2 + 1e-7f);
+          f = n2 / ((1.0f + n2) * sq);
+          fp = 1.0f / ((1.0f + n2) * sq) - f / (1.0f + n2) - 0.5f * f / (n2 + 1e-7f);
+        }
 #pragma unroll
-        for (int k = 0; k < T; ++k) {
-          const int e = (q * T + k) * 32 + ln;
-          const float t = tr[r * E + e];
-          const float gv = (r == R - 1 ? gout[e] : 0.f) + gacc[e];
-          gt[e] = f * gv + 2.0f * fp * dot * t;
-        }
-      }
-      __syncthreads();
-      if (SPLIT && rank == 0) {
-        for (int e = tid; e < E; e += NT) {
-          const int ln = e & 31, qk = e >> 5, q = qk / T, k = qk % T;
-          const int j = q * 32 + ln;
+        for (int k = 0; k < T; ++k) gtr[q][k] = f * gv[k] + 2.0f * fp * dot * tt[k];
+        if (SPLIT && rank == 0 && warp == 0) {
+          const int j = q * 32 + lane;
           if (j < O) {
-            const size_t o = (((size_t)frame * R + r) * O + j) * T + k;
-            p.gtT[o] = gt[e];
-            p.vaT[o] = vacc[r * E + e];
+            float4* gd = reinterpret_cast<float4*>(p.gtT + (((size_t)frame * R + r) * O + j) * T);
+            float4* vd = reinterpret_cast<float4*>(p.vaT + (((size_t)frame * R + r) * O + j) * T);
+#pragma unroll
+            for (int k4 = 0; k4 < T4; ++k4) {
+              gd[k4] = make_float4(gtr[q][k4 * 4], gtr[q][k4 * 4 + 1], gtr[q][k4 * 4 + 2], gtr[q][k4 * 4 + 3]);
+              vd[k4] = make_float4(va[q][k4 * 4], va[q][k4 * 4 + 1], va[q][k4 * 4 + 2], va[q][k4 * 4 + 3]);
+            }
           }
         }
       }
-      float va[OPL][T], gtr[OPL][T], gv_acc[OPL][T];
-#pragma unroll
-      for (int q = 0; q < OPL; ++q)
-#pragma unroll
-        for (int k = 0; k < T; ++k) {
-          va[q][k] = vacc[r * E + (q * T + k) * 32 + lane];
-          gtr[q][k] = gt[(q * T + k) * 32 + lane];
-          gv_acc[q][k] = 0.f;
-        }
       uint4 raw[RAWN];
-#pragma unroll
-      for (int m = 0; m < RAWN; ++m) raw[m] = raw0[m];
+      if (UM != 0 && i_lo + warp < i_hi) load_raw(i_lo + warp, raw);
       for (int i = i_lo + warp; i < i_hi; i += NW) {
         float u[OPL][T], a[OPL];
         if (UM != 0) {
@@ -547,14 +651,14 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
         float m = a[0];
 #pragma unroll
         for (int q = 1; q < OPL; ++q) m = fmaxf(m, a[q]);
-        m = bw_max(m);
+        m = UM != 0 ? bw_max_redux(m) : bw_max(m);
         float c[OPL], z = 0.f;
 #pragma unroll
         for (int q = 0; q < OPL; ++q) {
           c[q] = exp2f((a[q] - m) * LOG2E);
           z += c[q];
         }
-        const float inv = 1.0f / bw_sum(z);
+        const float inv = 1.0f / (UM != 0 ? bw_sum_redux<OPL>(z) : bw_sum(z));
         float gc[OPL], cg = 0.f;
 #pragma unroll
         for (int q = 0; q < OPL; ++q) {
@@ -624,38 +728,36 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
           }
         }
       }
-      if (UM != 0 && r == 0 && step > 0 && i_lo + warp < i_hi)
-        load_raw_at((long long)(sf - 1) * p.halfB + (b >> 1), i_lo + warp, raw0);
+      SRF_TK(6)
       // G_r = G_{r+1} + sum_i g_a u
 #pragma unroll
       for (int q = 0; q < OPL; ++q)
 #pragma unroll
         for (int k = 0; k < T; ++k) red[warp * E + (q * T + k) * 32 + lane] = gv_acc[q][k];
       __syncthreads();
-      for (int e = tid; e < E; e += NT) {
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) acc += red[w * E + e];
-        if (C > 1) tsum[par * E + e] = acc;
-        else gacc[e] += acc;
-      }
-      if (C > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cluster.sync();
-        for (int e = tid; e < E; e += NT) {
-          float v[8];
-#pragma unroll
-          for (int rk = 0; rk < 8; ++rk)
-            v[rk] = rk < C ? cluster.map_shared_rank(tsum, rk)[par * E + e] : 0.f;
-          gacc[e] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-        }
-        par ^= 1;
-      }
+      exchange([&](int e4, float4 tot) {
+        float4 g4 = reinterpret_cast<float4*>(gacc)[e4];
+        g4.x += tot.x;
+        g4.y += tot.y;
+        g4.z += tot.z;
+        g4.w += tot.w;
+        reinterpret_cast<float4*>(gacc)[e4] = g4;
+      });
       __syncthreads();
     }
     // gacc now holds dL/dVacc_0 = the BPTT carry into the previous frame (SDR)
+#ifdef SRF_BWD_PHASE_TIMERS
+    if (timing) {
+      const long long t7 = clock64();
+      unsigned long long* dd = p.dbg + (size_t)(blockIdx.x & 1023) * 8;
+      for (int n = 0; n < 6; ++n) dd[n] += (unsigned long long)(tk[n + 1] - tk[n]);
+      dd[6] += (unsigned long long)(t7 - tk[6]);
+      dd[7] += 1;
+    }
+#endif
   }
-  if (C > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's tsum
+#undef SRF_TK
+  if (C > 1) cg::this_cluster().sync();  // no CTA exits while a peer may still push into it
 }
 
 // ---------------------------------------------------------------------------------------
@@ -968,8 +1070,8 @@ void launch_fold_dx(const BwdParams& p, cudaStream_t stream) {
 template <int T, int OPL, int NW, int UM, bool SPLIT>
 static cudaError_t launch_bwd_variant(const BwdParams& p, int nchains, cudaStream_t stream) {
   const size_t E = (size_t)OPL * T * 32;
-  const size_t smem = sizeof(float) * ((UM == 0 ? (size_t)p.Ic * T : 0) + (NW + 2) * E +
-                                       (2 * BW_MAX_ITERS + 1) * E + 3 * E);
+  const size_t smem = sizeof(float) * (4 + (UM == 0 ? (size_t)p.Ic * T : 0) + (NW + 2 * p.C) * E +
+                                       (2 * BW_MAX_ITERS + 1) * E + 5 * E);
   auto kern = route_layer_bwd_kernel<T, OPL, NW, UM, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -988,12 +1090,19 @@ static cudaError_t launch_bwd_variant(const BwdParams& p, int nchains, cudaStrea
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-int route_layer_bwd_warps(int um) { return um == 1 ? SRF_BWD_NW_BF16 : (um == 2 ? SRF_BWD_NW_F32 : 8); }
+// warps per CTA of the sweep: 16 / 12 while the per-lane state (OPL*T values per array) leaves
+// room under the register budget, else 8
+int route_layer_bwd_warps(int um, int T, int OPL) {
+  if (um == 0 || T * OPL > 20) return 8;
+  return um == 1 ? SRF_BWD_NW_BF16 : SRF_BWD_NW_F32;
+}
 
 #define SRF_BWD(T_, OPL_)                                                                      \
   if (T == T_ && OPL == OPL_) {                                                                \
-    if (um == 1) return launch_bwd_variant<T_, OPL_, SRF_BWD_NW_BF16, 1, true>(p, nchains, stream); \
-    if (um == 2) return launch_bwd_variant<T_, OPL_, SRF_BWD_NW_F32, 2, true>(p, nchains, stream); \
+    if (um == 1)                                                                               \
+      return launch_bwd_variant<T_, OPL_, (T_ * OPL_ <= 20 ? SRF_BWD_NW_BF16 : 8), 1, true>(p, nchains, stream); \
+    if (um == 2)                                                                               \
+      return launch_bwd_variant<T_, OPL_, (T_ * OPL_ <= 20 ? SRF_BWD_NW_F32 : 8), 2, true>(p, nchains, stream);  \
     if (p.split) return launch_bwd_variant<T_, OPL_, 8, 0, true>(p, nchains, stream);         \
     return launch_bwd_variant<T_, OPL_, 8, 0, false>(p, nchains, stream);                     \
   }

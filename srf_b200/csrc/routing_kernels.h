@@ -80,8 +80,10 @@ struct BwdParams {
   int halfB;
   // cluster split of the BPTT sweep: C CTAs per chain, Ic input capsules each
   int C, Ic;
+  unsigned long long* dbg;  // optional phase timers [CTA][8] (clock64 sums), null = off
+  int l2_prefetch;          // sweep: prefetch the next frame's u_hat lines into L2
 };
-int route_layer_bwd_warps(int um);
+int route_layer_bwd_warps(int um, int T, int OPL);
 size_t dwdx_smem_bytes(int D, int d, int P, int FT);
 int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms);
 cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_t stream);

@@ -485,6 +485,9 @@ def test_layer_backward_matches_autograd(case, mode):
 def test_layer_backward_is_deterministic(mode, sdr):
   """dW / dbias / d_emb come from register sums and a fixed-order fold (no atomics): repeated
   launches must agree bit for bit -- also a race detector for the cluster exchange of the sweep."""
+  import os
+  if os.environ.get("SRF_BWD_ATOMICS", "0") not in ("", "0"):
+    pytest.skip("the fused atomics variant is not deterministic")
   from srf_b200 import routing
   B, S, H, d, O, D = (6, 40, 12, 20, 30, 20) if sdr else (3, 20, 12, 20, 30, 20)
   g = torch.Generator().manual_seed(5)

@@ -22,6 +22,9 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
 ]
 OBJDIR = os.path.join(HERE, "_build")
+# developer switches, e.g. SRF_NVCC_EXTRA="-DSRF_STREAM_PHASE_TIMERS -DSRF_BWD_PHASE_TIMERS" for the
+# clock64 phase timers read by tools/dev_phase_timers.py / tools/dev_bwd_phase_timers.py
+NVCC_FLAGS += os.environ.get("SRF_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -181,10 +181,24 @@ def load_checkpoint(model, path_ckpt: str, path_ckpt_epoch: Optional[int] = None
   return epoch_offset
 
 
+def canonicalize_state(state: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+  """Routing variables (`W%d` / `b%d`, any variant layout) -> canonical shapes; the rest unchanged."""
+  out = {k: np.asarray(v) for k, v in state.items()}
+  for name in list(out):
+    m = re.fullmatch(r"(.*/)?W(\d+)", name)
+    if m:
+      bname = (m.group(1) or "") + "b" + m.group(2)
+      if bname in out:
+        out[name], out[bname] = to_canonical(out[name], out[bname])
+  return out
+
+
 def average_states(states: Sequence[Dict[str, np.ndarray]]) -> Dict[str, np.ndarray]:
-  """Element-wise mean of the same-named arrays (average_ckpt_sr.py:137-146)."""
+  """Element-wise mean of the same-named arrays (average_ckpt_sr.py:137-146); routing variables
+  are brought to the canonical layout first, so checkpoints of different variants can be mixed."""
   if not states:
     raise ValueError("no checkpoints to average")
+  states = [canonicalize_state(s) for s in states]
   names = list(states[0])
   for s in states[1:]:
     if set(s) != set(names):

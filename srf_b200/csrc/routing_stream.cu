@@ -222,9 +222,15 @@ route_stream_kernel(const RouteParams p) {
           for (int q = 0; q < OPL; ++q)
 #pragma unroll
             for (int k = 0; k < T; ++k) ta[f][q][k] = 0.f;
+        // phase timers hold 12 live registers: compiled in only with -DSRF_STREAM_PHASE_TIMERS
+#ifdef SRF_STREAM_PHASE_TIMERS
         long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
         const bool timing = p.dbg != nullptr && tid == 0;
-        if (timing) tk0 = clock64();
+#define SRF_STK(v) if (timing) v = clock64();
+#else
+#define SRF_STK(v)
+#endif
+        SRF_STK(tk0)
 
         int rel_st = -1;  // stage still to be released
         for (int base = i_lo; base < i_hi; base += NSLOT) {
@@ -340,7 +346,7 @@ route_stream_kernel(const RouteParams p) {
           }
         }
 
-        if (timing) tk1 = clock64();
+        SRF_STK(tk1)
         // ---- reduce t over the capsule slots of this CTA -------------------------------------
 #pragma unroll
         for (int f = 0; f < FPW; ++f)
@@ -356,7 +362,7 @@ route_stream_kernel(const RouteParams p) {
         uint64_t* xf = &xfull[team * 2 + par];
         if (C > 1 && ttid == 0) ptx::mbar_arrive_expect_tx(xf, (uint32_t)(C - 1) * ET * 4);
         named_sync(bar_id, TT);
-        if (timing) tk2 = clock64();
+        SRF_STK(tk2)
         {
           // sum the NSLOT warp partials (float4 = 4 consecutive lanes) and publish the CTA partial:
           // own copy with a plain store, the peers' copies with st.async into their xbuf[par][rank]
@@ -388,14 +394,14 @@ route_stream_kernel(const RouteParams p) {
             if (lane == 0) ptx::mbar_arrive(xf);
           }
         }
-        if (timing) tk3 = clock64();
+        SRF_STK(tk3)
         if (C > 1) {
           ptx::mbar_wait(xf, (npass >> 1) & 1);
         } else {
           named_sync(bar_id, TT);
         }
         ++npass;
-        if (timing) tk4 = clock64();
+        SRF_STK(tk4)
 
         // ---- cluster sum (cooperative, float4) -> tot ------------------------------------------
         if (C > 1) {
@@ -414,7 +420,7 @@ route_stream_kernel(const RouteParams p) {
           named_sync(bar_id, TT);
         }
         const float* total = C > 1 ? tot : xbuf + (size_t)par * E;
-        if (timing) tk5 = clock64();
+        SRF_STK(tk5)
         // ---- squash (naive:248-253) + Vacc update: every consumer warp does this for its own
         // (member, lane) columns, the result feeds its registers directly; the slot-0 warps also
         // hand v to the output warps.
@@ -456,6 +462,7 @@ route_stream_kernel(const RouteParams p) {
             for (int f = 0; f < FPW; ++f) ptx::mbar_arrive(&vready[(f0 + f) * 2 + (s & 1)]);
           }
         }
+#ifdef SRF_STREAM_PHASE_TIMERS
         if (timing) {
           const long long tk6 = clock64();
           unsigned long long* d = p.dbg + (size_t)blockIdx.x * 8;
@@ -467,6 +474,8 @@ route_stream_kernel(const RouteParams p) {
           d[5] += (unsigned long long)(tk6 - tk5);  // squash + hand-off
           d[6] += 1;
         }
+#endif
+#undef SRF_STK
       }
     }
   } else if (warp <= NCW + 2) {

@@ -81,6 +81,16 @@ def test_load_checkpoint_follows_the_reference_rules(tmp_path):
     ck.load_checkpoint(m, str(tmp_path), strict=True)
 
 
+def test_average_mixes_variant_layouts(tmp_path):
+  a, b = ck.state_dict(FakeStack(1)), ck.state_dict(FakeStack(2))
+  ck.save_checkpoint(a, str(tmp_path), 1, variant="naive")
+  ck.save_checkpoint(b, str(tmp_path), 2, variant="einsum")
+  avg = ck.read_checkpoint(ck.average_checkpoints(str(tmp_path), 2))
+  assert avg["W0"].shape == (6, 5, 4, 3) and avg["b0"].shape == (6, 5, 4)
+  assert np.allclose(avg["W1"], (a["W1"] + b["W1"]) / 2, atol=1e-7)
+  assert np.allclose(avg["b1"], (a["b1"] + b["b1"]) / 2, atol=1e-7)
+
+
 def test_max_to_keep_prunes_old_checkpoints(tmp_path):
   s = ck.state_dict(FakeStack(0))
   for e in range(1, 6):

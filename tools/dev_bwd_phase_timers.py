@@ -1,4 +1,5 @@
-"""clock64 phase timers of the BPTT sweep (SRF_PHASE_TIMERS=1; last pass of the frame only is
+"""Needs a library built with SRF_NVCC_EXTRA=-DSRF_BWD_PHASE_TIMERS (python -m srf_b200.build --force).
+clock64 phase timers of the BPTT sweep (SRF_PHASE_TIMERS=1; last pass of the frame only is
 meaningful for ITER=1)."""
 import ctypes, os, sys
 os.environ['SRF_PHASE_TIMERS'] = '1'

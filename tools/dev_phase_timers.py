@@ -1,4 +1,5 @@
-"""Per-phase clock64 timers of the streaming routing kernel (SRF_PHASE_TIMERS=1)."""
+"""Needs a library built with SRF_NVCC_EXTRA=-DSRF_STREAM_PHASE_TIMERS (python -m srf_b200.build --force).
+Per-phase clock64 timers of the streaming routing kernel (SRF_PHASE_TIMERS=1)."""
 import ctypes, os, sys
 os.environ['SRF_PHASE_TIMERS'] = '1'
 sys.path.insert(0, '.')

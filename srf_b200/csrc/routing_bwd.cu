@@ -775,33 +775,36 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
 // ---------------------------------------------------------------------------------------
 namespace {
 struct DwdxPlan {
-  int FT, NT, NTc, P, aug;
+  int FT, NT, NC, P;  // frames per tile, threads, threads of the dW role (warp multiple), dx parts
   size_t smem;
 };
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 }  // namespace
 
 size_t dwdx_smem_bytes(int D, int d, int P, int FT) {
-  const int dp = (d + 3) & ~3;
-  return sizeof(float) * ((size_t)32 * D * dp + (size_t)FT * (D * 36 + 4) + round4(FT * (d + 1)) +
+  const int dp = (d + 3) & ~3, xrow = (d + 2) & ~1;
+  return sizeof(float) * ((size_t)32 * D * dp + (size_t)FT * (D * 36 + 4) + round4(FT * xrow) +
                           (size_t)P * FT * dp);
 }
 
 static bool dwdx_plan(const BwdParams& p, int max_smem, DwdxPlan* pl) {
   const int D = p.D, d = p.d, dp = (d + 3) & ~3, LQ = dp / 4;
-  pl->aug = D * (d + 1) <= 1024 ? 1 : 0;
-  pl->NTc = pl->aug ? D * (d + 1) : D * d;
-  int NT = (pl->NTc + 31) & ~31;
-  if (NT < 128) NT = 128;
-  pl->NT = NT;
+  const int ntc = D * ((d + 2) / 2);  // dW role: thread = (k, pair of l; l == d is the bias column)
+  pl->NC = (ntc + 31) & ~31;
   for (int FT = 32; FT >= 4; FT >>= 1) {
-    if (FT * LQ > NT) continue;
-    int P = NT / (FT * LQ);
-    if (P > 8) P = 8;
+    const int grp = (FT / 2) * LQ;  // dx role: thread = (pair of frames, 4 consecutive l, part)
+    // 384 threads leave 170 registers per thread (64 dW sums + the load groups of phase (b))
+    int P = (384 - pl->NC) / grp;
+    if (P < 1) P = (1024 - pl->NC) / grp;
+    if (P > 4) P = 4;
+    if (P < 1) continue;
+    const int NT = pl->NC + ((grp * P + 31) & ~31);
+    if (NT > 1024) continue;
     const size_t smem = dwdx_smem_bytes(D, d, P, FT);
     if (smem <= (size_t)max_smem) {
       pl->FT = FT;
       pl->P = P;
+      pl->NT = NT;
       pl->smem = smem;
       return true;
     }
@@ -823,16 +826,18 @@ int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms) {
   return (int)FS;
 }
 
-template <bool AUG, int MAXT, int MINB, int GB>
-__global__ void __launch_bounds__(MAXT, MINB) dwdx_from_saved_kernel(const BwdParams p, int FT, int ftsh,
-                                                                int NTc, int P) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) dwdx_from_saved_kernel(const BwdParams p, int FT, int NC, int P) {
+  constexpr int GB = 4;  // frames per load group of phase (b)
   extern __shared__ __align__(16) float sm[];
   const int D = p.D, d = p.d, dp = p.dp, R = p.iters, O = p.O, I = p.I, OP = p.OP, Tu = p.Tu;
   const int d1 = d + 1, LQ = dp >> 2, GS = D * 36 + 4, NT = blockDim.x;
+  const int xrow = (d + 2) & ~1;           // x row: d values, the bias column of ones, zero pad
+  const int L2n = (d + 2) >> 1;            // l pairs per k
   float* Ws = sm;                          // [32][D][dp]
   float* gus = Ws + 32 * D * dp;           // [FT][GS]: g_u[ft][k][j] at k*36 + j
-  float* xs = gus + FT * GS;               // [FT][d+1]
-  float* dxs = xs + round4(FT * d1);       // [P][FT][dp]
+  float* xs = gus + FT * GS;               // [FT][xrow]
+  float* dxs = xs + round4(FT * xrow);     // [P][FT][dp]
   const int i = blockIdx.x, fs = blockIdx.y, q = blockIdx.z, OPL = gridDim.z;
   const int jbase = q * 32;
   const int nj = (O - jbase) < 32 ? (O - jbase) : 32;
@@ -848,28 +853,28 @@ __global__ void __launch_bounds__(MAXT, MINB) dwdx_from_saved_kernel(const BwdPa
     if (j < nj && l < d) v = p.W[(((size_t)i * O + jbase + j) * D + k) * d + l];
     Ws[e] = v;
   }
-  const int lw = AUG ? d1 : d;
-  const bool dw_thread = tid < NTc;
-  const int k_dw = tid / lw, l_dw = tid - k_dw * lw;
-  float acc[32], accb[AUG ? 1 : 32];
+  // dW role: threads [0, NC): (k, l pair), the sums over the 32 output capsules in registers
+  const bool dw_thread = tid < D * L2n;
+  const int k_dw = tid / L2n, lp = tid - k_dw * L2n;
+  float acc0[32], acc1[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < (AUG ? 1 : 32); ++j) accb[j] = 0.f;
-  const int ft_dx = tid & (FT - 1), rest = tid >> ftsh;
+  for (int j = 0; j < 32; ++j) acc0[j] = acc1[j] = 0.f;
+  // dx role: threads [NC, NC + FT/2*LQ*P): (pair of frames, 4 consecutive l, part of the (k, j) range)
+  const int td = tid - NC, FH = FT >> 1;
+  const int ftp = td % FH, rest = td / FH;
   const int part = rest / LQ, lq = rest - part * LQ;
-  const bool dx_thread = part < P;
+  const bool dx_thread = td >= 0 && part < P;
 
   for (long long f0 = f_lo; f0 < f_hi; f0 += FT) {
     const int nf = (int)((f_hi - f0) < FT ? (f_hi - f0) : FT);
     // (a) window-gathered x of capsule i for the tile (+ the bias column of ones)
-    for (int e = tid; e < FT * d1; e += NT) {
-      const int ft = e / d1, l = e - ft * d1;
+    for (int e = tid; e < FT * xrow; e += NT) {
+      const int ft = e / xrow, l = e - ft * xrow;
       float v = 0.f;
       if (ft < nf) {
         if (l == d) {
           v = 1.f;
-        } else {
+        } else if (l < d) {
           const long long f = f0 + ft;
           const int b = (int)(f / p.S), s = (int)(f - (long long)b * p.S);
           const int src = s - p.lpad + w;
@@ -933,48 +938,55 @@ __global__ void __launch_bounds__(MAXT, MINB) dwdx_from_saved_kernel(const BwdPa
       }
     }
     __syncthreads();
-    // (c) dW / dbias
     if (dw_thread) {
+      // (c) dW / dbias: per frame one 8-byte x load and eight 16-byte g_u loads feed 64 FMAs
+      const float* xp = xs + 2 * lp;
+      const float* gp = gus + k_dw * 36;
       for (int ft = 0; ft < FT; ++ft) {
-        const float xv = xs[ft * d1 + l_dw];
-        const float4* row = reinterpret_cast<const float4*>(gus + ft * GS + k_dw * 36);
+        const float2 xv = *reinterpret_cast<const float2*>(xp + ft * xrow);
+        const float4* row = reinterpret_cast<const float4*>(gp + ft * GS);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 g4 = row[j4];
-          acc[j4 * 4 + 0] = fmaf(g4.x, xv, acc[j4 * 4 + 0]);
-          acc[j4 * 4 + 1] = fmaf(g4.y, xv, acc[j4 * 4 + 1]);
-          acc[j4 * 4 + 2] = fmaf(g4.z, xv, acc[j4 * 4 + 2]);
-          acc[j4 * 4 + 3] = fmaf(g4.w, xv, acc[j4 * 4 + 3]);
-          if (!AUG && l_dw == 0) {
-            accb[(j4 * 4 + 0) % (AUG ? 1 : 32)] += g4.x;
-            accb[(j4 * 4 + 1) % (AUG ? 1 : 32)] += g4.y;
-            accb[(j4 * 4 + 2) % (AUG ? 1 : 32)] += g4.z;
-            accb[(j4 * 4 + 3) % (AUG ? 1 : 32)] += g4.w;
-          }
+          acc0[j4 * 4 + 0] = fmaf(g4.x, xv.x, acc0[j4 * 4 + 0]);
+          acc0[j4 * 4 + 1] = fmaf(g4.y, xv.x, acc0[j4 * 4 + 1]);
+          acc0[j4 * 4 + 2] = fmaf(g4.z, xv.x, acc0[j4 * 4 + 2]);
+          acc0[j4 * 4 + 3] = fmaf(g4.w, xv.x, acc0[j4 * 4 + 3]);
+          acc1[j4 * 4 + 0] = fmaf(g4.x, xv.y, acc1[j4 * 4 + 0]);
+          acc1[j4 * 4 + 1] = fmaf(g4.y, xv.y, acc1[j4 * 4 + 1]);
+          acc1[j4 * 4 + 2] = fmaf(g4.z, xv.y, acc1[j4 * 4 + 2]);
+          acc1[j4 * 4 + 3] = fmaf(g4.w, xv.y, acc1[j4 * 4 + 3]);
         }
       }
-    }
-    // (d) dx partials
-    if (dx_thread) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* grow = gus + ft_dx * GS;
+    } else if (dx_thread) {
+      // (d) dx partials for two frames: per (k, 4 j) unit two g_u loads and four W loads feed 32 FMAs
+      float4 aA = make_float4(0.f, 0.f, 0.f, 0.f), aB = aA;
+      const float* gA = gus + ftp * GS;
+      const float* gB = gA + FH * GS;
       const float* wbase = Ws + lq * 4;
       const int wj = D * dp;  // floats per output capsule in Ws
       for (int un = part; un < 8 * D; un += P) {
         const int k = un >> 3, j4 = un & 7;
-        const float4 g4 = *reinterpret_cast<const float4*>(grow + k * 36 + j4 * 4);
-        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float4 a4 = *reinterpret_cast<const float4*>(gA + k * 36 + j4 * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(gB + k * 36 + j4 * 4);
+        const float ga[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float gb[4] = {b4.x, b4.y, b4.z, b4.w};
         const float* wp = wbase + j4 * 4 * wj + k * dp;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const float4 w4 = *reinterpret_cast<const float4*>(wp + jj * wj);
-          a.x = fmaf(gv[jj], w4.x, a.x);
-          a.y = fmaf(gv[jj], w4.y, a.y);
-          a.z = fmaf(gv[jj], w4.z, a.z);
-          a.w = fmaf(gv[jj], w4.w, a.w);
+          aA.x = fmaf(ga[jj], w4.x, aA.x);
+          aA.y = fmaf(ga[jj], w4.y, aA.y);
+          aA.z = fmaf(ga[jj], w4.z, aA.z);
+          aA.w = fmaf(ga[jj], w4.w, aA.w);
+          aB.x = fmaf(gb[jj], w4.x, aB.x);
+          aB.y = fmaf(gb[jj], w4.y, aB.y);
+          aB.z = fmaf(gb[jj], w4.z, aB.z);
+          aB.w = fmaf(gb[jj], w4.w, aB.w);
         }
       }
-      *reinterpret_cast<float4*>(dxs + ((size_t)part * FT + ft_dx) * dp + lq * 4) = a;
+      *reinterpret_cast<float4*>(dxs + ((size_t)part * FT + ftp) * dp + lq * 4) = aA;
+      *reinterpret_cast<float4*>(dxs + ((size_t)part * FT + ftp + FH) * dp + lq * 4) = aB;
     }
     __syncthreads();
     for (int e = tid; e < nf * dp; e += NT) {
@@ -984,13 +996,14 @@ __global__ void __launch_bounds__(MAXT, MINB) dwdx_from_saved_kernel(const BwdPa
       p.dxw[((((size_t)(f0 + ft)) * I + i) * OPL + q) * dp + l] = s;
     }
   }
-  if (dw_thread && k_dw < D) {
+  if (dw_thread) {
+    const int l0 = 2 * lp, l1 = l0 + 1;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < nj) {
         const size_t o = ((((size_t)fs * I + i) * O + jbase + j) * D + k_dw) * d1;
-        p.dwp[o + l_dw] = acc[j];
-        if (!AUG && l_dw == 0) p.dwp[o + d] = accb[j % (AUG ? 1 : 32)];
+        p.dwp[o + l0] = acc0[j];
+        if (l1 < d1) p.dwp[o + l1] = acc1[j];
       }
   }
 }
@@ -1013,19 +1026,17 @@ __global__ void reduce_dwp_kernel(const BwdParams p) {
 cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_t stream) {
   DwdxPlan pl;
   if (!dwdx_plan(p, max_smem, &pl)) return cudaErrorInvalidValue;
-  int ftsh = 0;
-  while ((1 << ftsh) < pl.FT) ++ftsh;
   dim3 grid(p.I, p.FS, p.OP / 32);
   cudaError_t e;
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (ee != cudaSuccess) return ee;
-    kern<<<grid, pl.NT, pl.smem, stream>>>(p, pl.FT, ftsh, pl.NTc, pl.P);
+    kern<<<grid, pl.NT, pl.smem, stream>>>(p, pl.FT, pl.NC, pl.P);
     return cudaSuccess;
   };
-  if (pl.aug && pl.NT <= 512) e = go(dwdx_from_saved_kernel<true, 512, 1, 4>);
-  else if (pl.aug) e = go(dwdx_from_saved_kernel<true, 1024, 1, 4>);
-  else e = go(dwdx_from_saved_kernel<false, 1024, 1, 4>);
+  if (pl.NT <= 384) e = go(dwdx_from_saved_kernel<384>);
+  else if (pl.NT <= 512) e = go(dwdx_from_saved_kernel<512>);
+  else e = go(dwdx_from_saved_kernel<1024>);
   if (e != cudaSuccess) return e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -371,6 +371,30 @@ def main():
       line["also"][name] = {"workload": ww["desc"], "ms_per_step": ms2,
                             "value": Bw * Sw / (ms2 / 1e3), "unit": "routing frames/s",
                             "note": "inputs resident; working set fits L2"}
+  if world == 1 and not args.no_also:
+    # cfg-4 (BASELINE.json configs[3]) at its per-GPU share on 8 GPUs: fwd + CTC + bwd + Adam of the
+    # WSJ-shaped stack on 8 x 375 routing frames, everything in the library (tools/train_bench.py
+    # runs the full global batch under torchrun with the NCCL gradient all-reduce)
+    from srf_b200 import training
+    w4 = WORKLOADS["cfg3"]
+    B4, S4 = 8, (w4["T"] + 3) // 4
+    st4 = RoutingStack(w4["L"], w4["PH"], w4["CH"], w4["class_n"], w4["DIM"], w4["DIM"], w4["DIM"],
+                       w4["lpad"], w4["rpad"], w4["iters"], w4["sdr"], device=dev, seed=0,
+                       inn_dropout=0.1, uhat_mode=args.uhat)
+    tr4 = training.TrainStep(st4, 64)
+    g4 = torch.Generator().manual_seed(4)
+    e4 = torch.randn(B4, S4, w4["PH"], w4["DIM"], generator=g4).to(dev)
+    lab4 = torch.randint(1, w4["class_n"] - 1, (B4, S4 // 3), generator=g4).to(dev)
+    il4 = torch.full((B4,), S4, device=dev)
+    ll4 = torch.full((B4,), S4 // 3, device=dev)
+    for _ in range(2):
+      tr4.step(e4, lab4, il4, ll4)
+    ms4 = timed(lambda i: tr4.step(e4, lab4, il4, ll4), 3) / 3
+    line["also"]["cfg4_train_step_share"] = {
+        "workload": "SRF-SDR WSJ-shaped training step (fwd + CTC loss + bwd + Adam), 8 x 375 routing "
+                    "frames = one GPU's share of the 64-utterance batch on 8 GPUs",
+        "ms_per_step": ms4, "value": B4 * S4 / (ms4 / 1e3), "unit": "routing frames/s"}
+    del st4, tr4
   if rank == 0 and not args.no_cpu_baseline and world == 1:
     n_utts, n_frames = cpu_sample_shape(w, big=True)
     fps, dt = cpu_reference_run(w, n_utts, n_frames, repeats=2)

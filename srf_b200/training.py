@@ -96,3 +96,40 @@ class FlatAdam:
                                   routing._ptr(self.v), self.flat.numel(), float(lr), self.beta1, self.beta2,
                                   self.eps, self.step_count, _stream(self.flat.device))
     _lib.check(self.h.lib, self.h._h, rc, "srf_adam_step")
+
+
+class TrainStep:
+  """One data-parallel training step of the routing stack, as `tfsr/trainer_sr.py:56-71` does it:
+  forward (training mode) + CTC loss scaled by 1/global_batch + backward + sum-all-reduce of the
+  flat gradient over the ranks (NCCL / gloo through torch.distributed, only when a process group
+  is initialised) + Adam with the warm-up schedule.  The stack's parameters become views into
+  the optimiser's flat buffer, so the update is one fused kernel."""
+
+  def __init__(self, stack, global_batch: int, k: float = 0.5, d_model: float = 256.0,
+               warmup_steps: float = 1200.0, group=None):
+    self.stack, self.global_batch, self.group = stack, int(global_batch), group
+    self.k, self.d_model, self.warmup_steps = k, d_model, warmup_steps
+    self.names = [n for n, _ in stack.named_parameters()]
+    self.opt = FlatAdam([t for _, t in stack.named_parameters()], handle=stack.handle)
+    views = dict(zip(self.names, self.opt.views))
+    n = len(stack.shapes)
+    stack.wgt = [views["W%d" % i] for i in range(n)]
+    stack.bias = [views["b%d" % i] for i in range(n)]
+    stack.ln_gamma = [views["ln_mid%d/gamma" % (i + 1)] for i in range(n)]
+    stack.ln_beta = [views["ln_mid%d/beta" % (i + 1)] for i in range(n)]
+    stack.lno_gamma, stack.lno_beta = views["ln_output/gamma"], views["ln_output/beta"]
+    stack.mark_weights_changed()
+    self.iteration = 0
+
+  def step(self, emb, labels, input_lengths, label_lengths, dropout_masks=None):
+    """Returns the summed CTC loss of this rank's utterances (device scalar)."""
+    import torch.distributed as dist
+    self.iteration += 1
+    loss, grads, _ = self.stack.ctc_train_step_grads(emb, labels, input_lengths, label_lengths,
+                                                     dropout_masks=dropout_masks)
+    flat = torch.cat([grads[k].reshape(-1) for k in self.names]).mul_(1.0 / self.global_batch)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+    self.opt.step(flat, warmup_lr(self.iteration, self.k, self.d_model, self.warmup_steps))
+    self.stack.mark_weights_changed()
+    return loss

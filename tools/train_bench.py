@@ -44,15 +44,7 @@ def main():
   stack = RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"], w["lpad"],
                        w["rpad"], w["iters"], w["sdr"], device=dev, seed=0, inn_dropout=0.1,
                        uhat_mode=args.uhat)
-  names = [n for n, _ in stack.named_parameters()]
-  opt = training.FlatAdam([t for _, t in stack.named_parameters()])
-  views = dict(zip(names, opt.views))
-  n = len(stack.shapes)
-  stack.wgt = [views["W%d" % i] for i in range(n)]
-  stack.bias = [views["b%d" % i] for i in range(n)]
-  stack.ln_gamma = [views["ln_mid%d/gamma" % (i + 1)] for i in range(n)]
-  stack.ln_beta = [views["ln_mid%d/beta" % (i + 1)] for i in range(n)]
-  stack.lno_gamma, stack.lno_beta = views["ln_output/gamma"], views["ln_output/beta"]
+  trainer = training.TrainStep(stack, args.batch)
   g = torch.Generator().manual_seed(1 + rank)
   emb = torch.randn(B, S, w["PH"], w["DIM"], generator=g).to(dev)
   Lab = max(1, S // 3)
@@ -63,13 +55,7 @@ def main():
   losses = []
 
   def step(it):
-    stack.mark_weights_changed()
-    loss, grads, _ = stack.ctc_train_step_grads(emb, labels, in_len, lab_len)
-    flat = torch.cat([grads[k].reshape(-1) for k in names]).mul_(1.0 / args.batch)
-    if world > 1:
-      dist.all_reduce(flat)
-    opt.step(flat, training.warmup_lr(it + 1, 0.5, 256, 1200))
-    losses.append(loss)
+    losses.append(trainer.step(emb, labels, in_len, lab_len))
 
   for it in range(args.warmup):
     step(it)
@@ -97,7 +83,7 @@ def main():
         "config": {"workload": "cfg4: " + w["desc"] + ", training step", "global_batch": args.batch,
                    "routing_frames_per_utterance": S, "uhat": args.uhat,
                    "parallelism": "dp%d (utterance shards, NCCL all-reduce of %d gradient floats)"
-                                  % (world, opt.flat.numel())},
+                                  % (world, trainer.opt.flat.numel())},
         "gpu_launches": h.launches - l0,
         "loss_first_last": [losses[0].item(), losses[-1].item()]}), flush=True)
   if world > 1:

@@ -835,7 +835,6 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
     p.C = C;
     p.Ic = (I + C - 1) / C;
     p.dbg = h->dbg;
-    p.l2_prefetch = getenv("SRF_BWD_NOPF") ? 0 : 1;
   }
   {
     KernelSpan span(h, 2, stream);

@@ -411,6 +411,8 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
     // streamed u_hat: frame pair index and which member of the pair this chain is
     const long long gg = (long long)sf * p.halfB + (b >> 1);
     const bool mem1 = (b & 1) != 0;
+    // bf16 -> fp32 of this chain's pair member: bytes (0, 0, lo, hi) of the selected half
+    const uint32_t usel = mem1 ? 0x3244u : 0x1044u;
     const size_t ustride_i = (size_t)OPL * T4 * 128 * 2;  // elements per (pair, i)
     auto load_raw_at = [&](long long gq, int i, uint4(&dst)[RAWN]) {
       if (UM == 1) {
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
             const uint32_t w[4] = {raw[m % RAWN].x, raw[m % RAWN].y, raw[m % RAWN].z, raw[m % RAWN].w};
 #pragma unroll
             for (int kin = 0; kin < 4; ++kin)
-              u[q][k4 * 4 + kin] = __uint_as_float(mem1 ? (w[kin] & 0xffff0000u) : (w[kin] << 16));
+              u[q][k4 * 4 + kin] = __uint_as_float(__byte_perm(w[kin], 0u, usel));  // one PRMT
           } else {
             const uint4 r0 = raw[(2 * m) % RAWN], r1 = raw[(2 * m + 1) % RAWN];
             u[q][k4 * 4 + 0] = __uint_as_float(mem1 ? r0.y : r0.x);
@@ -496,18 +498,6 @@ __global__ void __launch_bounds__(NW * 32) route_layer_bwd_kernel(const BwdParam
     }
     __syncthreads();
     if (step > 0) fetch_frame(step - 1);
-    // pull the next step's u_hat lines of this warp's capsules into L2 while this step computes
-    if (UM != 0 && step > 0 && p.l2_prefetch) {
-      constexpr int LINES = (int)(OPL * T4 * 128 * 2 * (UM == 1 ? 2 : 4) / 128);
-      const long long ggn = (long long)(sf - 1) * p.halfB + (b >> 1);
-      for (int i = i_lo + warp; i < i_hi; i += NW) {
-        const char* base = reinterpret_cast<const char*>(p.u) +
-                           ((size_t)ggn * I + i) * (size_t)(OPL * T4 * 128 * 2) * (UM == 1 ? 2 : 4);
-        for (int ln = lane; ln < LINES; ln += 32)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)ln * 128));
-      }
-    }
-
     SRF_TK(1)
     // ---------------- forward recompute: t_r, Vacc_r ----------------
     for (int r = 0; r < R; ++r) {

@@ -81,7 +81,6 @@ struct BwdParams {
   // cluster split of the BPTT sweep: C CTAs per chain, Ic input capsules each
   int C, Ic;
   unsigned long long* dbg;  // optional phase timers [CTA][8] (clock64 sums), null = off
-  int l2_prefetch;          // sweep: prefetch the next frame's u_hat lines into L2
 };
 int route_layer_bwd_warps(int um, int T, int OPL);
 size_t dwdx_smem_bytes(int D, int d, int P, int FT);

@@ -92,7 +92,8 @@ def load_state_dict(model, state: Dict[str, np.ndarray], variant: Optional[str] 
       t = named[nm]
       if tuple(t.shape) != val.shape:
         raise ValueError("%s: checkpoint shape %r, model shape %r" % (nm, val.shape, tuple(t.shape)))
-      t.copy_(torch.from_numpy(val))
+      with torch.no_grad():
+        t.copy_(torch.from_numpy(val))
       loaded.append(nm)
   for name, arr in state.items():
     if name in named and name not in loaded:
@@ -100,7 +101,8 @@ def load_state_dict(model, state: Dict[str, np.ndarray], variant: Optional[str] 
       val = np.asarray(arr, dtype=np.float32)
       if val.size != t.numel():
         raise ValueError("%s: checkpoint has %d elements, model %d" % (name, val.size, t.numel()))
-      t.copy_(torch.from_numpy(val.reshape(tuple(t.shape))))
+      with torch.no_grad():
+        t.copy_(torch.from_numpy(val.reshape(tuple(t.shape))))
       loaded.append(name)
   if strict:
     missing = sorted(set(named) - set(loaded))

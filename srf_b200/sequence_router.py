@@ -85,6 +85,16 @@ class RoutingStack:
     """Call after modifying W/bias in place: invalidates the packed-weight cache tag."""
     self._version = next(_version_counter)
 
+  def parameters(self):
+    return [t for _, t in self.named_parameters()]
+
+  def requires_grad_(self, flag: bool = True):
+    """Make the parameter tensors autograd leaves (for srf_b200.autograd.route_stack + a torch
+    optimiser)."""
+    for t in self.parameters():
+      t.requires_grad_(flag)
+    return self
+
   def load_oracle_params(self, p):
     """Copy parameters from an oracle StackParams (tests / bench)."""
     for i in range(len(self.shapes)):
@@ -226,6 +236,7 @@ class SequenceRouter:
         self.lpad, self.rpad, self.iter, self.is_context,
         inn_dropout=getattr(config, "train_inn_dropout", 0.1), device=self.device, seed=seed,
         uhat_mode=uhat_mode)
+    self.inp_dropout = float(getattr(config, "train_inp_dropout", 0.1))
     self.fe = {}   # front-end parameters, TF layouts; filled by load_frontend / first call
     self._fe_seed = seed
     if logger is not None:
@@ -277,8 +288,9 @@ class SequenceRouter:
     named = self.named_parameters()
     if len(weights) != len(named):
       raise ValueError("expected %d arrays, got %d" % (len(named), len(weights)))
-    for (name, t), w in zip(named, weights):
-      t.copy_(torch.as_tensor(w, dtype=torch.float32).reshape(t.shape))
+    with torch.no_grad():
+      for (name, t), w in zip(named, weights):
+        t.copy_(torch.as_tensor(w, dtype=torch.float32).reshape(t.shape))
     self.stack.mark_weights_changed()
 
   @property
@@ -286,44 +298,76 @@ class SequenceRouter:
     return [v for _, v in self.named_parameters()]
 
   # -- forward ---------------------------------------------------------------------------
-  def capsulate(self, inputs, input_lengths):
-    """fbank [B,T,feat] -> primary capsules emb [B,S,PH,PD] (naive:129-142, inference)."""
+  def capsulate(self, inputs, input_lengths, training: bool = False):
+    """fbank [B,T,feat] -> primary capsules emb [B,S,PH,PD] (naive:129-142).  training=True:
+    Dropout(0.2) after every front-end convolution (sequence_router.py:60-61,76-77; naive:81-82,
+    132), BatchNormalization with batch statistics and moving-average update (momentum 0.99),
+    input dropout `train_inp_dropout` (naive:142); all torch ops, differentiable."""
+    import torch.nn.functional as F
     x = routing_as_tensor(inputs, self.device)
     lens = torch.as_tensor(input_lengths).to(self.device)
     if not self.fe:
       self._init_frontend(x.shape[-1])
     f = self.fe
+    drop = (lambda t: F.dropout(t, 0.2, True)) if training else (lambda t: t)
     x = x[..., None]
     for li in range(self.cnn_n):                       # sequence_router.py:71-81
-      x1 = _conv2d_same_nhwc(x, f["cnn0_%d_kernel" % li], f["cnn0_%d_bias" % li], self.stride)
-      x2 = _conv2d_same_nhwc(x, f["cnn1_%d_kernel" % li], f["cnn1_%d_bias" % li], self.stride)
+      x1 = drop(_conv2d_same_nhwc(x, f["cnn0_%d_kernel" % li], f["cnn0_%d_bias" % li], self.stride))
+      x2 = drop(_conv2d_same_nhwc(x, f["cnn1_%d_kernel" % li], f["cnn1_%d_bias" % li], self.stride))
       x = torch.maximum(x1, x2)
       x = _feat_mask(x, lens, self.stride ** (li + 1))
-      x = (x - f["bn%d_mean" % li]) / torch.sqrt(f["bn%d_var" % li] + 1e-3) * f["bn%d_gamma" % li] \
-          + f["bn%d_beta" % li]
+      mean, var = f["bn%d_mean" % li], f["bn%d_var" % li]
+      if training:                                     # Keras BatchNormalization(axis=-1), training
+        bm = x.mean(dim=(0, 1, 2))
+        bv = x.var(dim=(0, 1, 2), unbiased=False)
+        with torch.no_grad():
+          mean.mul_(0.99).add_(bm.detach(), alpha=0.01)
+          var.mul_(0.99).add_(bv.detach(), alpha=0.01)
+        mean, var = bm, bv
+      x = (x - mean) / torch.sqrt(var + 1e-3) * f["bn%d_gamma" % li] + f["bn%d_beta" % li]
       x = _feat_mask(x, lens, self.stride ** (li + 1))
     B, S = x.shape[0], x.shape[1]
     emb = x.reshape(B, S, self.feat_dim * self.nfilt) @ f["dense_kernel"] + f["dense_bias"]
     emb = emb[..., None]                               # [B,S,PH,1]
-    emb = torch.maximum(_conv2d_same_nhwc(emb, f["encaps0_kernel"], f["encaps0_bias"], 1),
-                        _conv2d_same_nhwc(emb, f["encaps1_kernel"], f["encaps1_bias"], 1))
+    emb = torch.maximum(drop(_conv2d_same_nhwc(emb, f["encaps0_kernel"], f["encaps0_bias"], 1)),
+                        drop(_conv2d_same_nhwc(emb, f["encaps1_kernel"], f["encaps1_bias"], 1)))
     emb = _feat_mask(emb, lens, self.stride ** 2)
     n2 = (emb * emb).sum(-1, keepdim=True)             # squash, naive:248-253
     emb = (n2 / (1.0 + n2)) * emb / torch.sqrt(n2 + 1e-7)
     flat = emb.reshape(B, S, self.caps_inp_n * self.caps_inp_d)
     flat = torch.nn.functional.layer_norm(flat, (flat.shape[-1],), f["ln_input_gamma"],
                                           f["ln_input_beta"], eps=1e-3)
-    return flat.reshape(B, S, self.caps_inp_n, self.caps_inp_d).contiguous()
+    emb = flat.reshape(B, S, self.caps_inp_n, self.caps_inp_d)
+    if training and self.inp_dropout > 0:
+      emb = F.dropout(emb, self.inp_dropout, True)     # naive:142
+    return emb.contiguous()
+
+  # parameters that receive gradients (BatchNorm moving statistics do not)
+  def parameters(self):
+    if not self.fe:
+      raise RuntimeError("front-end parameters are created at the first call (or load_frontend)")
+    return [v for k, v in sorted(self.fe.items()) if not k.endswith(("_mean", "_var"))] + \
+        self.stack.parameters()
+
+  def requires_grad_(self, flag: bool = True):
+    for t in self.parameters():
+      t.requires_grad_(flag)
+    return self
 
   def __call__(self, inputs, input_lengths=None, training=False, **kwargs):
+    """training=False: inference (no autograd).  training=True (tfsr/trainer_sr.py:63): dropouts
+    on, BatchNorm batch statistics, and the result is attached to the torch autograd graph --
+    torch differentiates the front-end, the CUDA library the routing stack
+    (srf_b200.autograd.route_stack); call `requires_grad_()` once to make the parameters leaves."""
     if input_lengths is None:
       raise ValueError("input_lengths is required (naive:121)")
     if training:
-      raise NotImplementedError(
-          "SequenceRouter front-end: training mode (dropout + BatchNorm batch statistics) is not "
-          "built yet; RoutingStack.forward(training=True) covers the routing path")
-    emb = self.capsulate(inputs, input_lengths)
-    return self.stack.forward(emb, training=False)
+      from . import autograd
+      emb = self.capsulate(inputs, input_lengths, training=True)
+      return autograd.route_stack(self.stack, emb)
+    with torch.no_grad():
+      emb = self.capsulate(inputs, input_lengths)
+      return self.stack.forward(emb, training=False)
 
   call = __call__
 

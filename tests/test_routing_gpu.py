@@ -584,3 +584,74 @@ def test_checkpoint_round_trip_and_average_on_the_stack(tmp_path):
   ck.load_state_dict(c, ck.read_checkpoint(ck.average_checkpoints(str(tmp_path), 2)))
   for (n, t), (_, ta), (_, tb) in zip(c.named_parameters(), a.named_parameters(), b.named_parameters()):
     assert torch.allclose(t, (ta + tb) / 2, atol=1e-7), n
+
+
+def test_autograd_bridge_matches_oracle_autograd():
+  """srf_b200.autograd.route_stack: loss.backward() through the CUDA stack fills emb.grad and the
+  parameters' .grad like autograd of the float64 oracle."""
+  from srf_b200 import RoutingStack, autograd
+  L, PH, CH, class_n, DIM, lpad, rpad, iters, B, S = 2, 8, 5, 7, 8, 1, 1, 2, 2, 6
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1)
+  p32 = o.init_params(shapes, class_n, seed=6, random_ln=True)
+  p = p32.to(torch.float64)
+  g = torch.Generator().manual_seed(12)
+  emb = torch.randn(B, S, PH, DIM, generator=g, dtype=torch.float64)
+  wl = torch.randn(B, S, class_n, generator=g, dtype=torch.float64)
+  masks = [((torch.rand(B, S, s[1], s[2], generator=g) < 0.9).double() / 0.9) for s in shapes]
+  leaves = p.W + p.bias + p.ln_gamma + p.ln_beta + [p.lno_gamma, p.lno_beta, emb]
+  for t in leaves:
+    t.requires_grad_(True)
+  (o.route_stack(emb, p, lpad, rpad, iters, True, dropout_masks=masks) * wl).sum().backward()
+  stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, True, seed=0)
+  stack.load_oracle_params(p32)
+  stack.requires_grad_()
+  e = emb.detach().float().cuda().requires_grad_(True)
+  logits = autograd.route_stack(stack, e, dropout_masks=[m.float().cuda() for m in masks])
+  (logits * wl.float().cuda()).sum().backward()
+  assert rel_err(e.grad, emb.grad) < 5e-4
+  for i in range(L):
+    assert rel_err(stack.wgt[i].grad, p.W[i].grad) < 5e-4, i
+    assert rel_err(stack.bias[i].grad, p.bias[i].grad) < 5e-4, i
+    assert rel_err(stack.ln_gamma[i].grad, p.ln_gamma[i].grad) < 5e-4, i
+  assert rel_err(stack.lno_gamma.grad, p.lno_gamma.grad) < 5e-4
+  assert rel_err(stack.lno_beta.grad, p.lno_beta.grad) < 5e-4
+
+
+def test_sequence_router_trains_end_to_end_with_a_torch_optimiser():
+  """training=True (tfsr/trainer_sr.py:63): dropouts + BatchNorm batch statistics in the torch
+  front-end, routing stack differentiated by the CUDA library; a few Adam steps lower the CTC loss."""
+  import types
+  from srf_b200 import SequenceRouter
+  cfg = types.SimpleNamespace(
+      model_conv_layer_num=2, feat_dim=20, model_conv_filter_num=4, model_encoder_num=2,
+      model_caps_iter=1, model_caps_window_lpad=1, model_caps_window_rpad=1, model_caps_context=True,
+      model_caps_primary_num=10, model_caps_primary_dim=8, model_caps_convolution_num=6,
+      model_caps_convolution_dim=8, model_caps_class_dim=8, train_inp_dropout=0.05, train_inn_dropout=0.05)
+  class_n, B, T = 9, 4, 48
+  model = SequenceRouter(cfg, None, class_n, seed=3)
+  g = torch.Generator().manual_seed(1)
+  feats = torch.randn(B, T, 20, generator=g)
+  lens = torch.tensor([48, 44, 40, 36])
+  labels = torch.randint(1, class_n - 1, (B, 4), generator=g).cuda()
+  lab_len = torch.full((B,), 4)
+  model(feats, input_lengths=lens)                      # creates the front-end parameters
+  bn_before = model.fe["bn0_mean"].clone()
+  model.requires_grad_()
+  opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+  losses = []
+  for _ in range(25):
+    opt.zero_grad()
+    logits = model(feats, input_lengths=lens, training=True)
+    assert logits.requires_grad and logits.shape == (B, 12, class_n)
+    loss = torch.nn.functional.ctc_loss(torch.log_softmax(logits, -1).transpose(0, 1), labels,
+                                        (lens + 3) // 4, lab_len, blank=class_n - 1, reduction="mean",
+                                        zero_infinity=True)
+    loss.backward()
+    opt.step()
+    losses.append(loss.item())
+  assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+  assert sum(losses[-5:]) / 5 < 0.85 * sum(losses[:5]) / 5, losses
+  assert not torch.equal(model.fe["bn0_mean"], bn_before)     # moving statistics were updated
+  out1 = model(feats, input_lengths=lens)                      # inference: deterministic, no graph
+  out2 = model(feats, input_lengths=lens)
+  assert not out1.requires_grad and torch.equal(out1, out2)

@@ -166,7 +166,7 @@ def main():
   ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other configs")
-  ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "bf16"],
+  ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "bf16", "fp32x3"],
                   help="u_hat arithmetic: bf16 = tcgen05 TF32 MMA + bf16 u_hat storage (default), "
                        "tf32 = same with fp32 storage, fp32 = exact FP32 CUDA-core kernel")
   args = ap.parse_args()
@@ -296,7 +296,7 @@ def main():
                for k, v in kprof.items()}
   dom = max(("uhat_gemm", "routing"), key=lambda k: kprof[k][0])
   dom_ms_launch = kprof[dom][0] / max(1, kprof[dom][1])
-  esize = {"fp32": 0, "tf32": 4, "bf16": 2}[args.uhat]
+  esize = {"fp32": 0, "tf32": 4, "bf16": 2, "fp32x3": 4}[args.uhat]
   uhat_elems = sum(I * O * D for (I, O, D, d) in shapes_of(w))          # per routing frame, all layers
   traffic = None
   try:
@@ -335,11 +335,13 @@ def main():
       "metric": "routing_frames_per_sec", "value": value, "unit": "routing frames/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-      "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.uhat], "data": "synthetic",
+      "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "fp32x3": "f32"}[args.uhat], "data": "synthetic",
       "config": {"workload": w["desc"], "global_batch": B * world, "routing_frames_per_utt": S,
                  "fbank_frames_per_sec": value * 4,
                  "uhat": {"fp32": "FP32 CUDA cores, fused", "tf32": "tcgen05 TF32 MMA, fp32 u_hat in HBM",
-                          "bf16": "tcgen05 TF32 MMA, bf16 u_hat in HBM (1e-2 tolerance mode)"}[args.uhat],
+                          "bf16": "tcgen05 TF32 MMA, bf16 u_hat in HBM (1e-2 tolerance mode)",
+                          "fp32x3": "tcgen05 3 x TF32 split MMA (fp32-class), fp32 u_hat in HBM "
+                                    "(1e-4 tolerance mode)"}[args.uhat],
                  "parallelism": "dp%d (utterance shards, no collective)" % world,
                  "l2": "working set per step (inputs %d MB x2 rotating + weights %d MB + u_hat %d MB/layer) > 126 MB L2"
                        % (host_emb[0].numel() * 4 >> 20, weights >> 20,

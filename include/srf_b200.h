@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRF_B200_VERSION 101 /* major*10000 + minor*100 + patch */
+#define SRF_B200_VERSION 102 /* major*10000 + minor*100 + patch */
 
 typedef struct srf_handle srf_handle;
 
@@ -33,7 +33,9 @@ typedef struct srf_handle srf_handle;
 enum {
   SRF_UHAT_FP32 = 0, /* FP32 FFMA on CUDA cores, fp32 weights                     */
   SRF_UHAT_TF32 = 1, /* tensor cores, TF32 operands, fp32 accumulate (tcgen05)     */
-  SRF_UHAT_BF16 = 2  /* tensor cores, BF16 operands, fp32 accumulate (tcgen05)     */
+  SRF_UHAT_BF16 = 2, /* tensor cores, BF16 operands, fp32 accumulate (tcgen05)     */
+  SRF_UHAT_FP32X3 = 3 /* tensor cores, 3 x TF32 split (W_hi x_hi + W_lo x_hi + W_hi x_lo): fp32-class
+                         u_hat (rel. error ~1e-6), fp32 storage -- the 1e-4 parity class on tcgen05 */
 };
 
 /*

@@ -21,6 +21,7 @@ struct PackedWeights {
   const float* bias = nullptr;
   int I = 0, O = 0, D = 0, d = 0, T = 0, OP = 0;
   uint64_t version = 0;
+  int x3 = 0;
   float* Wp = nullptr;
   float* Bp = nullptr;
   size_t bytes = 0;
@@ -300,7 +301,7 @@ static int validate_layer(srf_handle* h, const srf_layer_desc* L, bool fwd = tru
   if (fwd && L->head_gamma && !L->out_logits)
     return fail(h, -1, "head requested but out_logits is NULL");
   if (L->uhat_mode != SRF_UHAT_FP32 && L->uhat_mode != SRF_UHAT_TF32 &&
-      L->uhat_mode != SRF_UHAT_BF16)
+      L->uhat_mode != SRF_UHAT_BF16 && L->uhat_mode != SRF_UHAT_FP32X3)
     return fail(h, -4, "unknown uhat_mode %d", L->uhat_mode);
   if (L->O > 128) return fail(h, -3, "O = %d output capsules > 128 is not supported", L->O);
   if (L->D > 32 || L->d > 32)
@@ -370,7 +371,7 @@ static int get_packed(srf_handle* h, const srf_layer_desc* L, int I, int T, int 
 namespace {
 struct UhatGeom {
   int I, T, OPL, MT, KC, NB, NS, NBT, NST, Bpad;
-  bool bf16;
+  bool bf16, x3;
   size_t bytes;
 };
 }  // namespace
@@ -381,8 +382,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
-  if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_BF16)
-    return fail(h, -4, "tensor-core u_hat needs uhat_mode TF32 or BF16");
+  if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_BF16 &&
+      L->uhat_mode != SRF_UHAT_FP32X3)
+    return fail(h, -4, "tensor-core u_hat needs uhat_mode TF32, BF16 or FP32X3");
   if (L->d % 4 != 0)
     return fail(h, -3, "tensor-core u_hat needs d %% 4 == 0 (got d=%d); use SRF_UHAT_FP32", L->d);
   if ((reinterpret_cast<uintptr_t>(L->emb) & 15) != 0)
@@ -401,8 +403,9 @@ static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
   g->NBT = (L->B + g->NB - 1) / g->NB;
   g->NST = (L->S + g->NS - 1) / g->NS;
   g->bf16 = L->uhat_mode == SRF_UHAT_BF16;
+  g->x3 = L->uhat_mode == SRF_UHAT_FP32X3;
   g->bytes = (size_t)L->S * (g->Bpad / 2) * g->I * g->MT * 128 * 2 * (g->bf16 ? 2 : 4);
-  const size_t smem = srf::uhat_gemm_smem_bytes(g->MT, g->KC);
+  const size_t smem = srf::uhat_gemm_smem_bytes(g->MT, g->KC, g->x3 ? 1 : 0);
   if (smem > (size_t)h->max_smem)
     return fail(h, -3, "u_hat GEMM tile does not fit in shared memory (O=%d, D=%d, d=%d)", L->O,
                 L->D, L->d);
@@ -413,13 +416,14 @@ static int get_packed_mma(srf_handle* h, const srf_layer_desc* L, const UhatGeom
                           cudaStream_t stream, const PackedWeights** out) {
   PackedWeights* hit = nullptr;
   for (auto& pw : h->packed_mma)
-    if (pw.W == L->W && pw.bias == L->bias) {
+    if (pw.W == L->W && pw.bias == L->bias && pw.x3 == (g.x3 ? 1 : 0)) {
       hit = &pw;
       break;
     }
-  const size_t nW = (size_t)g.I * g.MT * g.KC * 512, nB = (size_t)g.I * g.MT * 128;
+  const size_t nW = (size_t)g.I * g.MT * g.KC * 512 * (g.x3 ? 2 : 1), nB = (size_t)g.I * g.MT * 128;
   const size_t bytes = (nW + nB) * sizeof(float);
-  const bool same = hit && hit->I == g.I && hit->O == L->O && hit->D == L->D && hit->d == L->d;
+  const bool same = hit && hit->I == g.I && hit->O == L->O && hit->D == L->D && hit->d == L->d &&
+                    hit->x3 == (g.x3 ? 1 : 0);
   if (same && L->weights_version != 0 && hit->version == L->weights_version) {
     *out = hit;
     return 0;
@@ -451,10 +455,11 @@ static int get_packed_mma(srf_handle* h, const srf_layer_desc* L, const UhatGeom
   hit->D = L->D;
   hit->d = L->d;
   hit->version = L->weights_version;
+  hit->x3 = g.x3 ? 1 : 0;
   {
     KernelSpan span(h, 0, stream);
     srf::launch_pack_weights_mma(L->W, L->bias, hit->Wp, hit->Bp, g.I, L->O, L->D, L->d, g.T, g.OPL,
-                                 g.KC, stream);
+                                 g.KC, g.x3 ? 1 : 0, stream);
   }
   h->launches++;
   cudaError_t e = cudaGetLastError();
@@ -517,6 +522,7 @@ static int compute_uhat(srf_handle* h, const srf_layer_desc* L, const UhatGeom& 
   p.NST = g.NST;
   p.Bpad = g.Bpad;
   p.store_bf16 = g.bf16 ? 1 : 0;
+  p.x3 = g.x3 ? 1 : 0;
   p.items = (long long)g.I * g.NBT * g.NST;
   cudaError_t e;
   {
@@ -659,7 +665,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
     int Cs = C;
     if (Cs * groups > h->num_sms) Cs = pow2_floor(h->num_sms / groups > 0 ? h->num_sms / groups : 1);
     const size_t stage = srf::route_stream_stage_bytes(T, OPL, um == 1);
-    const size_t fixed = srf::route_stream_fixed_smem(T, OPL, Cs, 16);
+    const size_t fixed = srf::route_stream_fixed_smem(T, OPL, um == 1, Cs, 16);
     if (fixed + 2 * stage <= (size_t)h->max_smem) {
       int nstage = (int)(((size_t)h->max_smem - fixed) / stage);
       if (nstage > 16) nstage = 16;
@@ -682,7 +688,8 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
       snprintf(nm, sizeof(nm),
                "uhat_gemm_kernel(tcgen05 tf32) + route_stream_kernel<T=%d,OPL=%d,NW=%d,%s> C=%d "
                "groups=%d stages=%d smem=%zu",
-               T, OPL, SRF_NW, um == 1 ? "bf16" : "fp32", Cs, groups, nstage, smem_s);
+               T, OPL, srf::route_stream_nslot(T, OPL, um == 1), um == 1 ? "bf16" : "fp32", Cs, groups,
+               nstage, smem_s);
       h->last_kernel = nm;
       return 0;
     }

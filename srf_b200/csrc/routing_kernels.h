@@ -112,6 +112,7 @@ struct UhatParams {
   int NBT, NST;     // number of tiles along b and s
   int Bpad;         // B rounded up to even
   int store_bf16;
+  int x3;           // 3 x TF32 split: Wm holds [hi tile][lo tile] per capsule, x is split in-kernel
   long long items;  // I * NBT * NST
 };
 
@@ -124,14 +125,15 @@ cudaError_t launch_route_layer(const RouteParams& p, int T, int OPL, int F, int 
                                size_t smem_bytes, int um, cudaStream_t stream);
 
 // streaming routing kernel over a materialised u_hat (routing_stream.cu)
-size_t route_stream_fixed_smem(int T, int OPL, int C, int max_stages);
+int route_stream_nslot(int T, int OPL, bool bf16);
+size_t route_stream_fixed_smem(int T, int OPL, bool bf16, int C, int max_stages);
 size_t route_stream_stage_bytes(int T, int OPL, bool bf16);
 cudaError_t launch_route_stream(const RouteParams& p, int T, int OPL, bool bf16, int groups,
                                 size_t smem_bytes, cudaStream_t stream);
 
 void launch_pack_weights_mma(const float* W, const float* bias, float* Wm, float* Bm, int I, int O,
-                             int D, int d, int T, int OPL, int KC, cudaStream_t stream);
-size_t uhat_gemm_smem_bytes(int MT, int KC);
+                             int D, int d, int T, int OPL, int KC, int x3, cudaStream_t stream);
+size_t uhat_gemm_smem_bytes(int MT, int KC, int x3);
 void launch_unpack_uhat(const void* u, float* out, int B, int S, int I, int O, int D, int T, int OPL,
                         int Bpad, int is_bf16, cudaStream_t stream);
 

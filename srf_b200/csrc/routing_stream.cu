@@ -20,6 +20,8 @@
 // peers' mbarriers -- no cluster-wide barrier on the per-frame critical path.
 
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "routing_kernels.h"
@@ -592,16 +594,16 @@ route_stream_kernel(const RouteParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <int T, int OPL, int FPW, bool BF16>
+template <int T, int OPL, int NSLOT, int FPW, bool BF16>
 static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_t smem_bytes,
                                          cudaStream_t stream) {
-  auto kern = route_stream_kernel<T, OPL, SRF_NW, FPW, BF16>;
+  auto kern = route_stream_kernel<T, OPL, NSLOT, FPW, BF16>;
   cudaError_t err =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * p.C));
-  cfg.blockDim = dim3((SRF_NW * (2 / FPW) + 3) * 32);
+  cfg.blockDim = dim3((NSLOT * (2 / FPW) + 3) * 32);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -615,20 +617,43 @@ static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_
 }
 
 // fixed (non-ring) shared memory of the streaming kernel
-size_t route_stream_fixed_smem(int T, int OPL, int C, int max_stages) {
+// capsule slots per ring stage (= consumer warps per pair member).  fp32 u_hat storage doubles the
+// registers a warp holds per capsule: with one member per warp, 6 slots (15 warps, 136 registers)
+// keep that variant spill-free where 8 slots (19 warps, 104 registers) spill.
+int route_stream_nslot(int T, int OPL, bool bf16) {
+  static const int f32_slots = [] {
+    const char* e = getenv("SRF_STREAM_NSLOT_F32");
+    const int v = e ? atoi(e) : 6;
+    return v == 8 ? 8 : 6;
+  }();
+  static const int bf16_slots = [] {
+    const char* e = getenv("SRF_STREAM_NSLOT_BF16");
+    const int v = e ? atoi(e) : 8;
+    return v == 6 ? 6 : 8;
+  }();
+  const bool one_member_per_warp = T * OPL <= 20;
+  if (bf16) return (one_member_per_warp && T * OPL > 8) ? bf16_slots : SRF_NW;
+  return (one_member_per_warp && T * OPL > 8) ? f32_slots : SRF_NW;
+}
+size_t route_stream_fixed_smem(int T, int OPL, bool bf16, int C, int max_stages) {
   const size_t E = (size_t)2 * OPL * T * 32;
-  return sizeof(float) * ((size_t)SRF_NW * E + (size_t)2 * C * E + 3 * E) +
+  return sizeof(float) * ((size_t)route_stream_nslot(T, OPL, bf16) * E + (size_t)2 * C * E + 3 * E) +
          sizeof(uint64_t) * (2 * (size_t)max_stages + 12) + 128;
 }
 size_t route_stream_stage_bytes(int T, int OPL, bool bf16) {
-  return (size_t)SRF_NW * OPL * (T / 4) * 128 * 2 * (bf16 ? 2 : 4);
+  return (size_t)route_stream_nslot(T, OPL, bf16) * OPL * (T / 4) * 128 * 2 * (bf16 ? 2 : 4);
 }
 
 // variants with a per-lane state of <= 20 floats per pair member run one member per warp
-#define SRF_STREAM(T_, OPL_, FPW_)                                                            \
-  if (T == T_ && OPL == OPL_)                                                                 \
-    return bf16 ? launch_stream_variant<T_, OPL_, FPW_, true>(p, groups, smem_bytes, stream)  \
-                : launch_stream_variant<T_, OPL_, FPW_, false>(p, groups, smem_bytes, stream);
+#define SRF_STREAM(T_, OPL_, FPW_)                                                                  \
+  if (T == T_ && OPL == OPL_) {                                                                     \
+    if (bf16 && route_stream_nslot(T_, OPL_, true) == 6)                                            \
+      return launch_stream_variant<T_, OPL_, 6, FPW_, true>(p, groups, smem_bytes, stream);         \
+    if (bf16) return launch_stream_variant<T_, OPL_, SRF_NW, FPW_, true>(p, groups, smem_bytes, stream); \
+    if (route_stream_nslot(T_, OPL_, false) == 6)                                                   \
+      return launch_stream_variant<T_, OPL_, 6, FPW_, false>(p, groups, smem_bytes, stream);        \
+    return launch_stream_variant<T_, OPL_, SRF_NW, FPW_, false>(p, groups, smem_bytes, stream);     \
+  }
 
 cudaError_t launch_route_stream(const RouteParams& p, int T, int OPL, bool bf16, int groups,
                                 size_t smem_bytes, cudaStream_t stream) {

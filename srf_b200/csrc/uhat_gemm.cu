@@ -35,14 +35,17 @@ namespace srf {
 
 // ---------------------------------------------------------------------------------------
 // weight packing for the MMA:  W[I,O,D,d], bias[I,O,D] ->
-//   Wm float[i][mt][c][r][4]   mt = jb*(T/4) + k4, r = (j%32)*4 + k%4, c = 16-byte K chunk
+//   Wm float[i][part][mt][c][r][4]   mt = jb*(T/4) + k4, r = (j%32)*4 + k%4, c = 16-byte K chunk
 //   Bm float[i][mt][r]
+// part: one tile (W rounded to TF32) or, for the 3 x TF32 split, two: hi = rn_tf32(W) and
+// lo = rn_tf32(W - hi)
 // ---------------------------------------------------------------------------------------
 __global__ void pack_weights_mma_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                         float* __restrict__ Wm, float* __restrict__ Bm, int I, int O,
-                                        int D, int d, int T, int OPL, int KC) {
+                                        int D, int d, int T, int OPL, int KC, int x3) {
   const int MT = OPL * (T / 4);
-  const long long nW = (long long)I * MT * KC * 128 * 4;
+  const int P = x3 ? 2 : 1;
+  const long long nW = (long long)I * P * MT * KC * 128 * 4;
   const long long nB = (long long)I * MT * 128;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nW + nB; e += stride) {
@@ -54,7 +57,9 @@ __global__ void pack_weights_mma_kernel(const float* __restrict__ W, const float
       const int c = (int)(q % KC);
       q /= KC;
       const int mt = (int)(q % MT);
-      const int i = (int)(q / MT);
+      q /= MT;
+      const int part = (int)(q % P);
+      const int i = (int)(q / P);
       const int jb = mt / (T / 4), k4 = mt % (T / 4);
       const int j = jb * 32 + r / 4, k = k4 * 4 + (r & 3), l = c * 4 + li;
       float v = 0.f;
@@ -63,6 +68,10 @@ __global__ void pack_weights_mma_kernel(const float* __restrict__ W, const float
       // weight operand carries no truncation bias
       uint32_t tf;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tf) : "f"(v));
+      if (part == 1) {
+        const float lo = v - __uint_as_float(tf);  // exact in fp32
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tf) : "f"(lo));
+      }
       Wm[e] = __uint_as_float(tf);
     } else {
       long long q = e - nW;
@@ -80,11 +89,11 @@ __global__ void pack_weights_mma_kernel(const float* __restrict__ W, const float
 }
 
 void launch_pack_weights_mma(const float* W, const float* bias, float* Wm, float* Bm, int I, int O,
-                             int D, int d, int T, int OPL, int KC, cudaStream_t stream) {
-  const long long n = (long long)I * OPL * (T / 4) * 128 * (KC * 4 + 1);
+                             int D, int d, int T, int OPL, int KC, int x3, cudaStream_t stream) {
+  const long long n = (long long)I * OPL * (T / 4) * 128 * (KC * 4 * (x3 ? 2 : 1) + 1);
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weights_mma_kernel<<<blocks, 256, 0, stream>>>(W, bias, Wm, Bm, I, O, D, d, T, OPL, KC);
+  pack_weights_mma_kernel<<<blocks, 256, 0, stream>>>(W, bias, Wm, Bm, I, O, D, d, T, OPL, KC, x3);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -94,27 +103,34 @@ constexpr int UH_N = 64;         // frames per MMA (TMEM columns per slot)
 constexpr int UH_SLOTS = 8;      // 8 x 64 = 512 TMEM columns
 constexpr int UH_XSTAGES = 4;    // x-tile ring depth
 constexpr int UH_EPI_WARPS = 8;   // 2 per TMEM lane quarter, 32 columns each
-constexpr int UH_THREADS = (2 + UH_EPI_WARPS) * 32;
+constexpr int UH_THREADS = (3 + UH_EPI_WARPS) * 32;  // + one splitter warp (3 x TF32 mode)
 
-template <bool BF16>
+// X3: 3 x TF32 split.  The A operand arrives as two tiles (hi, lo); a splitter warp rewrites each
+// x tile in place as x_hi = x with the 13 low mantissa bits cleared (exactly TF32-representable)
+// and writes x_lo = x - x_hi (exact) to a second buffer; the MMA issuer accumulates
+// W_hi x_hi + W_lo x_hi + W_hi x_lo in the same TMEM slot: u_hat carries fp32-class error.
+template <bool BF16, bool X3>
 __global__ void __launch_bounds__(UH_THREADS, 1)
 uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = p.MT, KC = p.KC;
-  const uint32_t a_bytes = (uint32_t)MT * KC * 2048u;   // whole W[i]
+  const uint32_t a_tile = (uint32_t)MT * KC * 2048u;    // one image of W[i]
+  const uint32_t a_bytes = X3 ? 2u * a_tile : a_tile;   // hi (+ lo)
   const uint32_t x_bytes = (uint32_t)KC * UH_N * 16u;   // one x tile
 
   uint8_t* sA = smem_raw;
   uint8_t* sX = sA + a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)UH_XSTAGES * x_bytes);
+  uint8_t* sXlo = sX + (size_t)UH_XSTAGES * x_bytes;    // X3 only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXlo + (X3 ? (size_t)UH_XSTAGES * x_bytes : 0));
   uint64_t* x_full = bars;                       // [XSTAGES]
   uint64_t* x_empty = x_full + UH_XSTAGES;       // [XSTAGES]
   uint64_t* t_full = x_empty + UH_XSTAGES;       // [SLOTS]
   uint64_t* t_empty = t_full + UH_SLOTS;         // [SLOTS]
   uint64_t* w_full = t_empty + UH_SLOTS;         // [1]
   uint64_t* w_empty = w_full + 1;                // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + 1);
+  uint64_t* x_split = w_empty + 1;               // [XSTAGES] x_hi / x_lo ready (X3)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_split + UH_XSTAGES);
 
   const long long per = (p.items + gridDim.x - 1) / gridDim.x;
   const long long item_lo = (long long)blockIdx.x * per;
@@ -126,6 +142,7 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     for (int s = 0; s < UH_XSTAGES; ++s) {
       ptx::mbar_init(&x_full[s], 1);
       ptx::mbar_init(&x_empty[s], 1);
+      ptx::mbar_init(&x_split[s], 1);
     }
     for (int s = 0; s < UH_SLOTS; ++s) {
       ptx::mbar_init(&t_full[s], 1);
@@ -187,7 +204,7 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
           cur_i = i;
         }
         const int st = n_x % UH_XSTAGES;
-        ptx::mbar_wait(&x_full[st], (n_x / UH_XSTAGES) & 1);
+        ptx::mbar_wait(X3 ? &x_split[st] : &x_full[st], (n_x / UH_XSTAGES) & 1);
         ptx::tc_fence_after();
         for (int mt = 0; mt < MT; ++mt) {
           const int slot = n_t % UH_SLOTS;
@@ -200,6 +217,15 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
             const uint64_t bdesc = ptx::make_smem_desc(
                 sX_addr + (uint32_t)st * x_bytes + (uint32_t)ks * (2u * UH_N * 16u), UH_N * 16u, 128u);
             ptx::mma_tf32_ss(d_addr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+            if (X3) {
+              const uint64_t adesc_lo = ptx::make_smem_desc(
+                  sA_addr + a_tile + (uint32_t)mt * KC * 2048u + (uint32_t)ks * 4096u, 2048u, 128u);
+              const uint64_t bdesc_lo = ptx::make_smem_desc(
+                  ptx::smem_u32(sXlo) + (uint32_t)st * x_bytes + (uint32_t)ks * (2u * UH_N * 16u),
+                  UH_N * 16u, 128u);
+              ptx::mma_tf32_ss(d_addr, adesc_lo, bdesc, idesc, 1u);
+              ptx::mma_tf32_ss(d_addr, adesc, bdesc_lo, idesc, 1u);
+            }
           }
           ptx::mma_commit(&t_full[slot]);
           ++n_t;
@@ -208,6 +234,32 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
         ++n_x;
         const bool last_of_i = (item + 1 == item_hi) || ((int)((item + 1) / ntiles) != i);
         if (last_of_i) ptx::mma_commit(w_empty);
+      }
+    }
+  } else if (warp >= 2 + UH_EPI_WARPS) {
+    // ================= splitter (X3): x -> x_hi (in place), x_lo =================
+    if (X3) {
+      uint32_t n_x = 0;
+      const int n4 = (int)(x_bytes / 16u);
+      for (long long item = item_lo; item < item_hi; ++item) {
+        const int st = n_x % UH_XSTAGES;
+        ptx::mbar_wait(&x_full[st], (n_x / UH_XSTAGES) & 1);
+        uint4* px = reinterpret_cast<uint4*>(sX + (size_t)st * x_bytes);
+        float4* pl = reinterpret_cast<float4*>(sXlo + (size_t)st * x_bytes);
+        for (int e = lane; e < n4; e += 32) {
+          const uint4 v = px[e];
+          const uint4 hi = make_uint4(v.x & 0xffffe000u, v.y & 0xffffe000u, v.z & 0xffffe000u,
+                                      v.w & 0xffffe000u);
+          px[e] = hi;
+          pl[e] = make_float4(__uint_as_float(v.x) - __uint_as_float(hi.x),
+                              __uint_as_float(v.y) - __uint_as_float(hi.y),
+                              __uint_as_float(v.z) - __uint_as_float(hi.z),
+                              __uint_as_float(v.w) - __uint_as_float(hi.w));
+        }
+        ptx::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&x_split[st]);
+        ++n_x;
       }
     }
   } else {
@@ -287,15 +339,17 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
   }
 }
 
-size_t uhat_gemm_smem_bytes(int MT, int KC) {
-  return (size_t)MT * KC * 2048 + (size_t)UH_XSTAGES * KC * UH_N * 16 +
-         sizeof(uint64_t) * (2 * UH_XSTAGES + 2 * UH_SLOTS + 2) + 16;
+size_t uhat_gemm_smem_bytes(int MT, int KC, int x3) {
+  const size_t mul = x3 ? 2 : 1;
+  return mul * ((size_t)MT * KC * 2048 + (size_t)UH_XSTAGES * KC * UH_N * 16) +
+         sizeof(uint64_t) * (3 * UH_XSTAGES + 2 * UH_SLOTS + 2) + 16;
 }
 
 cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int num_sms,
                              cudaStream_t stream) {
-  const size_t smem = uhat_gemm_smem_bytes(p.MT, p.KC);
-  auto kern = p.store_bf16 ? uhat_gemm_kernel<true> : uhat_gemm_kernel<false>;
+  const size_t smem = uhat_gemm_smem_bytes(p.MT, p.KC, p.x3);
+  auto kern = p.x3 ? uhat_gemm_kernel<false, true>
+                   : (p.store_bf16 ? uhat_gemm_kernel<true, false> : uhat_gemm_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long grid = p.items < num_sms ? p.items : num_sms;

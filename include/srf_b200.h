@@ -175,8 +175,8 @@ int srf_adam_step(srf_handle* h, float* param, const float* grad, float* m, floa
 /*
  * prediction vectors alone: window gather + u_hat = W.x + bias (naive:150-159) for every frame,
  * written in the reference's [B,S,I,O,D] layout (naive:158), fp32.  Uses emb, W, bias, B,S,H,d,
- * O,D, lpad, rpad and uhat_mode of the descriptor: SRF_UHAT_TF32 / SRF_UHAT_BF16 run the tcgen05
- * GEMM (u_hat kept in fp32 / bf16 before the copy-out).  Requires d % 4 == 0.
+ * O,D, lpad, rpad and uhat_mode of the descriptor: SRF_UHAT_TF32 / SRF_UHAT_BF16 / SRF_UHAT_FP32X3
+ * run the tcgen05 GEMM (u_hat kept in fp32 / bf16 / fp32 before the copy-out).  Requires d % 4 == 0.
  */
 int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* layer, float* out_uhat, void* stream);
 

@@ -617,9 +617,11 @@ static cudaError_t launch_stream_variant(const RouteParams& p, int groups, size_
 }
 
 // fixed (non-ring) shared memory of the streaming kernel
-// capsule slots per ring stage (= consumer warps per pair member).  fp32 u_hat storage doubles the
-// registers a warp holds per capsule: with one member per warp, 6 slots (15 warps, 136 registers)
-// keep that variant spill-free where 8 slots (19 warps, 104 registers) spill.
+// capsule slots per ring stage (= consumer warps per pair member).  With one member per warp,
+// 6 slots (15 warps, 136 registers, more ring stages) beat 8 slots (19 warps, 104 registers):
+// measured on cfg-3 with 4 / 5 / 6 / 7 / 8 slots: 28.6 / 26.9 / 25.4 / 29.1 / 26.4 ms per step in
+// bf16 storage, and 42.5 vs 54.9 ms (6 vs 8) in fp32 storage, where the 8-slot build spills.
+// SRF_STREAM_NSLOT_BF16 / SRF_STREAM_NSLOT_F32 = 8 select the wider build.
 int route_stream_nslot(int T, int OPL, bool bf16) {
   static const int f32_slots = [] {
     const char* e = getenv("SRF_STREAM_NSLOT_F32");
@@ -628,8 +630,8 @@ int route_stream_nslot(int T, int OPL, bool bf16) {
   }();
   static const int bf16_slots = [] {
     const char* e = getenv("SRF_STREAM_NSLOT_BF16");
-    const int v = e ? atoi(e) : 8;
-    return v == 6 ? 6 : 8;
+    const int v = e ? atoi(e) : 6;
+    return v == 8 ? 8 : 6;
   }();
   const bool one_member_per_warp = T * OPL <= 20;
   if (bf16) return (one_member_per_warp && T * OPL > 8) ? bf16_slots : SRF_NW;

@@ -633,7 +633,16 @@ int route_stream_nslot(int T, int OPL, bool bf16) {
     const int v = e ? atoi(e) : 6;
     return v == 8 ? 8 : 6;
   }();
+  // two members per warp (large per-lane state): 4 slots make the D = 32 variant spill-free
+  // (cfg-5 DIM=32: routing 53.0 -> 33.7 ms); the O > 32 variants measure the same or slightly
+  // worse with 4 slots and stay at 8.  SRF_STREAM_NSLOT_FPW2 = 4 | 8 overrides.
+  static const int fpw2_slots = [] {
+    const char* e = getenv("SRF_STREAM_NSLOT_FPW2");
+    const int v = e ? atoi(e) : 0;
+    return (v == 4 || v == 8) ? v : 0;
+  }();
   const bool one_member_per_warp = T * OPL <= 20;
+  if (!one_member_per_warp) return fpw2_slots ? fpw2_slots : (T == 32 ? 4 : 8);
   if (bf16) return (one_member_per_warp && T * OPL > 8) ? bf16_slots : SRF_NW;
   return (one_member_per_warp && T * OPL > 8) ? f32_slots : SRF_NW;
 }
@@ -649,6 +658,9 @@ size_t route_stream_stage_bytes(int T, int OPL, bool bf16) {
 // variants with a per-lane state of <= 20 floats per pair member run one member per warp
 #define SRF_STREAM(T_, OPL_, FPW_)                                                                  \
   if (T == T_ && OPL == OPL_) {                                                                     \
+    if (route_stream_nslot(T_, OPL_, bf16) == 4 && FPW_ == 2)                                       \
+      return bf16 ? launch_stream_variant<T_, OPL_, 4, 2, true>(p, groups, smem_bytes, stream)      \
+                  : launch_stream_variant<T_, OPL_, 4, 2, false>(p, groups, smem_bytes, stream);    \
     if (bf16 && route_stream_nslot(T_, OPL_, true) == 6)                                            \
       return launch_stream_variant<T_, OPL_, 6, FPW_, true>(p, groups, smem_bytes, stream);         \
     if (bf16) return launch_stream_variant<T_, OPL_, SRF_NW, FPW_, true>(p, groups, smem_bytes, stream); \

@@ -115,6 +115,21 @@ class LayerArgs:
   keep: list = field(default_factory=list)
 
 
+def exact_mode(d: int, O: int, D: int, emb_aligned: bool = True) -> str:
+  """The fastest u_hat mode of the 1e-4 parity class for a layer shape: "fp32x3" (3 x TF32 split on
+  the tensor cores) where its tiles exist and fit in shared memory, else "fp32" (fused CUDA-core
+  kernel).  Mirrors uhat_geometry / uhat_gemm_smem_bytes of csrc/capi.cu, csrc/uhat_gemm.cu."""
+  if d % 4 != 0 or not emb_aligned or O > 128 or D > 32 or d > 32:
+    return "fp32"
+  T = 8 if D <= 8 else (16 if D <= 16 else (20 if D <= 20 else 32))
+  OPL = (O + 31) // 32
+  if (T == 16 and OPL > 2) or (T == 20 and OPL > 2) or (T == 32 and OPL > 1):
+    return "fp32"
+  MT, KC = OPL * (T // 4), 2 * ((d + 7) // 8)
+  smem = 2 * (MT * KC * 2048 + 4 * KC * 64 * 16) + 8 * (3 * 4 + 2 * 8 + 2) + 16
+  return "fp32x3" if smem <= 227 * 1024 else "fp32"
+
+
 def _fill_desc(desc: _lib.LayerDesc, a: LayerArgs, emb, B, S, H, d, out_caps, out_logits):
   I, O, D, d_w = a.W.shape
   window = a.lpad + a.rpad + 1
@@ -128,7 +143,10 @@ def _fill_desc(desc: _lib.LayerDesc, a: LayerArgs, emb, B, S, H, d, out_caps, ou
       raise ValueError("%s has %d elements, expected %d" % (name, t.numel(), n))
   if a.dropout_mask is not None and a.dropout_mask.numel() != B * S * O * D:
     raise ValueError("dropout_mask has %d elements, expected %d" % (a.dropout_mask.numel(), B * S * O * D))
-  if a.uhat_mode not in _lib.UHAT_MODES:
+  mode = a.uhat_mode
+  if mode == "exact":   # 1e-4 class, fastest available for this shape
+    mode = exact_mode(d, O, D, emb is None or emb.data_ptr() % 16 == 0)
+  if mode not in _lib.UHAT_MODES:
     raise ValueError("unknown uhat_mode %r" % (a.uhat_mode,))
   desc.emb = _ptr(emb)
   desc.W, desc.bias = _ptr(a.W), _ptr(a.bias)
@@ -139,7 +157,7 @@ def _fill_desc(desc: _lib.LayerDesc, a: LayerArgs, emb, B, S, H, d, out_caps, ou
   desc.B, desc.S, desc.H, desc.d, desc.O, desc.D = B, S, H, d, O, D
   desc.lpad, desc.rpad, desc.iters = a.lpad, a.rpad, a.iters
   desc.sdr, desc.mask_class0 = int(bool(a.sdr)), int(bool(a.mask_class0))
-  desc.uhat_mode = _lib.UHAT_MODES[a.uhat_mode]
+  desc.uhat_mode = _lib.UHAT_MODES[mode]
   desc.ln_eps, desc.length_eps = a.ln_eps, a.length_eps
   desc.weights_version = a.weights_version
   return O, D

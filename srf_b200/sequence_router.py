@@ -41,7 +41,7 @@ class RoutingStack:
 
   def __init__(self, enc_num: int, ph: int, ch: int, class_n: int, pd: int, cd: int, vd: int,
                lpad: int, rpad: int, iters: int, sdr: bool, inn_dropout: float = 0.1,
-               device=None, seed: Optional[int] = None, uhat_mode: str = "fp32",
+               device=None, seed: Optional[int] = None, uhat_mode: str = "exact",
                length_eps: float = routing.LENGTH_EPS):
     if enc_num < 1:
       raise ValueError("model_encoder_num must be >= 1")
@@ -216,7 +216,7 @@ class SequenceRouter:
   path.
   """
 
-  def __init__(self, config, logger, class_n, device=None, seed=None, uhat_mode="fp32"):
+  def __init__(self, config, logger, class_n, device=None, seed=None, uhat_mode="exact"):
     self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
     import math

@@ -672,3 +672,23 @@ def test_sequence_router_trains_end_to_end_with_a_torch_optimiser():
   out1 = model(feats, input_lengths=lens)                      # inference: deterministic, no graph
   out2 = model(feats, input_lengths=lens)
   assert not out1.requires_grad and torch.equal(out1, out2)
+
+
+def test_default_mode_is_exact_class_on_the_tensor_cores():
+  """RoutingStack's default uhat_mode="exact": the 3 x TF32 tensor path where it fits (1e-4 class),
+  the fused FP32 kernel elsewhere."""
+  from srf_b200 import RoutingStack
+  g = torch.Generator().manual_seed(2)
+  for DIM, expect in ((8, "uhat_gemm_kernel"), (6, "route_layer_kernel")):
+    L, PH, CH, class_n, B, S = 2, 12, 6, 9, 3, 7
+    shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, 3)
+    p32 = o.init_params(shapes, class_n, seed=1, random_ln=True)
+    emb = torch.randn(B, S, PH, DIM, generator=g)
+    ref = o.route_stack(emb.double(), p32.to(torch.float64), 1, 1, 1, True)
+    stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, 1, 1, 1, True, seed=0)
+    assert stack.uhat_mode == "exact"
+    stack.load_oracle_params(p32)
+    logits = stack.forward(emb.cuda())
+    torch.cuda.synchronize()
+    assert expect in stack.handle.last_kernel, stack.handle.last_kernel
+    assert rel_err(logits, ref) < 1e-4

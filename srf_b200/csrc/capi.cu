@@ -396,8 +396,16 @@ static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
   g->MT = g->OPL * (g->T / 4);
   g->KC = 2 * ((L->d + 7) / 8);
   g->Bpad = (L->B + 1) & ~1;
-  int nb = 2;
-  while (nb < 64 && nb < g->Bpad) nb *= 2;
+  // utterances per 64-frame tile: the power of two that wastes the fewest tile slots on the batch
+  // edge (B = 43: NB = 4 covers 44 slots, NB = 64 would cover 64), larger on ties
+  int nb = 2, best_cover = 1 << 30;
+  for (int c = 64; c >= 2; c >>= 1) {
+    const int cover = (g->Bpad + c - 1) / c * c;
+    if (cover < best_cover) {
+      best_cover = cover;
+      nb = c;
+    }
+  }
   g->NB = nb;
   g->NS = 64 / nb;
   g->NBT = (L->B + g->NB - 1) / g->NB;

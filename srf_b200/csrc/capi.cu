@@ -392,7 +392,7 @@ static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
   const int window = L->lpad + L->rpad + 1;
   g->I = window * L->H;
   g->T = L->D <= 8 ? 8 : (L->D <= 16 ? 16 : (L->D <= 20 ? 20 : 32));  // = routing kernel's T
-  g->OPL = (L->O + 31) / 32;
+  g->OPL = L->O <= 32 ? 1 : (L->O <= 64 ? 2 : 4);  // = the routing kernels' output capsules per lane
   g->MT = g->OPL * (g->T / 4);
   g->KC = 2 * ((L->d + 7) / 8);
   g->Bpad = (L->B + 1) & ~1;
@@ -847,6 +847,11 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
     while (C > 1 && (I + C - 1) / C < nw / 2) C /= 2;
     if (h->force_C > 0 && h->force_C <= 8) C = h->force_C;
     if (!p.split) C = 1;
+    // the exchange buffers grow with the cluster size: narrow the cluster until the CTA fits
+    while (C > 1 && srf::route_layer_bwd_smem_bytes(T, OPL, um, (I + C - 1) / C, C) > (size_t)h->max_smem)
+      C /= 2;
+    if (srf::route_layer_bwd_smem_bytes(T, OPL, um, (I + C - 1) / C, C) > (size_t)h->max_smem)
+      return fail(h, -3, "backward sweep does not fit in shared memory (I=%d, O=%d, D=%d)", I, L->O, L->D);
     p.C = C;
     p.Ic = (I + C - 1) / C;
     p.dbg = h->dbg;

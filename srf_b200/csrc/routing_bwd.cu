@@ -1094,6 +1094,13 @@ static cudaError_t launch_bwd_variant(const BwdParams& p, int nchains, cudaStrea
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
+size_t route_layer_bwd_smem_bytes(int T, int OPL, int um, int Ic, int C) {
+  const size_t E = (size_t)OPL * T * 32;
+  const size_t NW = (size_t)route_layer_bwd_warps(um, T, OPL);
+  return sizeof(float) * (4 + (um == 0 ? (size_t)Ic * T : 0) + (NW + 2 * (size_t)C) * E +
+                          (2 * BW_MAX_ITERS + 1) * E + 5 * E);
+}
+
 // warps per CTA of the sweep: 16 / 12 while the per-lane state (OPL*T values per array) leaves
 // room under the register budget, else 8
 int route_layer_bwd_warps(int um, int T, int OPL) {

@@ -83,6 +83,7 @@ struct BwdParams {
   unsigned long long* dbg;  // optional phase timers [CTA][8] (clock64 sums), null = off
 };
 int route_layer_bwd_warps(int um, int T, int OPL);
+size_t route_layer_bwd_smem_bytes(int T, int OPL, int um, int Ic, int C);
 size_t dwdx_smem_bytes(int D, int d, int P, int FT);
 int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms);
 cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_t stream);

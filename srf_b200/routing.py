@@ -122,7 +122,7 @@ def exact_mode(d: int, O: int, D: int, emb_aligned: bool = True) -> str:
   if d % 4 != 0 or not emb_aligned or O > 128 or D > 32 or d > 32:
     return "fp32"
   T = 8 if D <= 8 else (16 if D <= 16 else (20 if D <= 20 else 32))
-  OPL = (O + 31) // 32
+  OPL = 1 if O <= 32 else (2 if O <= 64 else 4)   # the kernels' output capsules per lane
   if (T == 16 and OPL > 2) or (T == 20 and OPL > 2) or (T == 32 and OPL > 1):
     return "fp32"
   MT, KC = OPL * (T // 4), 2 * ((d + 7) // 8)

@@ -252,6 +252,8 @@ TENSOR_LAYER_CASES = [
     (1, 6, 5, 32, 6, 32, 4, 4),
     (2, 4, 9, 8, 100, 8, 0, 1),
     (3, 4, 9, 4, 10, 12, 1, 0),        # d != D
+    (2, 4, 6, 8, 70, 8, 1, 0),         # 64 < O <= 96: four output capsules per lane, one empty
+    (5, 7, 2, 12, 70, 4, 1, 0),        # found by tests/dev/fuzz_parity.py (GEMM / routing lane layout)
 ]
 
 
@@ -445,6 +447,7 @@ BWD_CASES = [
     (1, 4, 6, 8, 40, 8, 0, 0, 2, False, True),     # 2 output capsules per lane
     (4, 70, 4, 4, 5, 4, 1, 1, 1, True, False),     # 280 frames: several tiles and frame splits
     (3, 90, 3, 4, 6, 8, 0, 1, 2, False, True),     # odd batch, DR, 270 frames
+    (5, 5, 7, 4, 33, 20, 2, 2, 1, True, False),    # D=20 with O > 32: the sweep's cluster must shrink to fit
 ]
 # tolerance of (forward capsules, gradients) per u_hat mode; the tensor modes differentiate the
 # function they compute (rounded u_hat), so their gradients carry the same rounding class

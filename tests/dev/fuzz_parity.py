@@ -2,7 +2,7 @@
 (forward capsules, and gradients of a random linear functional against autograd of the float64
 oracle for a subset).  Run on a GPU box from the repository root:
 
-    python tests/dev/fuzz_parity.py [n_cases] [seed]
+    python tests/dev/fuzz_parity.py [n_cases] [seed] [scale]     (scale multiplies B, S, H ranges)
 """
 import random
 import sys
@@ -15,6 +15,7 @@ from srf_b200 import routing
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+SCALE = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 TOL = {"fp32": 1e-4, "fp32x3": 1e-4, "tf32": 1e-2, "bf16": 2e-2}
 GTOL = {"fp32": 3e-4, "fp32x3": 3e-4, "tf32": 2e-2, "bf16": 8e-2}
 
@@ -33,7 +34,7 @@ for case in range(N):
   OPL = (O + 31) // 32
   if (T >= 16 and OPL > 2) or (T == 32 and OPL > 1):
     O = rng.choice([2, 5, 9, 30, 32])
-  B, S, H = rng.randint(1, 6), rng.randint(1, 9), rng.randint(1, 14)
+  B, S, H = rng.randint(1, 6 * SCALE), rng.randint(1, 9 * SCALE), rng.randint(1, 14 * SCALE)
   lpad, rpad = rng.randint(0, 3), rng.randint(0, 3)
   iters, sdr, last = rng.randint(1, 4), rng.random() < 0.6, rng.random() < 0.4
   I = (lpad + rpad + 1) * H

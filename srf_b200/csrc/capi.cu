@@ -370,7 +370,7 @@ static int get_packed(srf_handle* h, const srf_layer_desc* L, int I, int T, int 
 // ---------------------------------------------------------------------------------------
 namespace {
 struct UhatGeom {
-  int I, T, OPL, MT, KC, NB, NS, NBT, NST, Bpad;
+  int I, T, OPL, MT, KC, NB, NS, NBT, NST, Bpad, MTG, NG;
   bool bf16, x3;
   size_t bytes;
 };
@@ -413,8 +413,13 @@ static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
   g->bf16 = L->uhat_mode == SRF_UHAT_BF16;
   g->x3 = L->uhat_mode == SRF_UHAT_FP32X3;
   g->bytes = (size_t)L->S * (g->Bpad / 2) * g->I * g->MT * 128 * 2 * (g->bf16 ? 2 : 4);
-  const size_t smem = srf::uhat_gemm_smem_bytes(g->MT, g->KC, g->x3 ? 1 : 0);
-  if (smem > (size_t)h->max_smem)
+  // M tiles of W[i] resident at a time: all of them, or as many as fit (the x tiles are then
+  // streamed once per group)
+  g->MTG = g->MT;
+  while (g->MTG > 1 && srf::uhat_gemm_smem_bytes(g->MTG, g->KC, g->x3 ? 1 : 0) > (size_t)h->max_smem)
+    g->MTG = (g->MTG + 1) / 2;
+  g->NG = (g->MT + g->MTG - 1) / g->MTG;
+  if (srf::uhat_gemm_smem_bytes(g->MTG, g->KC, g->x3 ? 1 : 0) > (size_t)h->max_smem)
     return fail(h, -3, "u_hat GEMM tile does not fit in shared memory (O=%d, D=%d, d=%d)", L->O,
                 L->D, L->d);
   return 0;
@@ -531,7 +536,9 @@ static int compute_uhat(srf_handle* h, const srf_layer_desc* L, const UhatGeom& 
   p.Bpad = g.Bpad;
   p.store_bf16 = g.bf16 ? 1 : 0;
   p.x3 = g.x3 ? 1 : 0;
-  p.items = (long long)g.I * g.NBT * g.NST;
+  p.MTG = g.MTG;
+  p.NG = g.NG;
+  p.items = (long long)g.I * g.NG * g.NBT * g.NST;
   cudaError_t e;
   {
     KernelSpan span(h, 1, stream);

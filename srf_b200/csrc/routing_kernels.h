@@ -108,13 +108,14 @@ struct UhatParams {
   const float* Bm;  // packed bias       [I][MT][128]
   void* u;          // u_hat out         [S*Bpad/2 frame pairs][I][MT][128][2]  bf16 or fp32
   int I, MT, KC;    // KC = 16-byte K chunks per row (2 per tf32 MMA)
+  int MTG, NG;      // M tiles resident in shared memory at a time, number of such groups per capsule
   int B, S, H, lpad;
   int NB, NS;       // frame tile = NB utterances x NS time steps (NB*NS = 64)
   int NBT, NST;     // number of tiles along b and s
   int Bpad;         // B rounded up to even
   int store_bf16;
   int x3;           // 3 x TF32 split: Wm holds [hi tile][lo tile] per capsule, x is split in-kernel
-  long long items;  // I * NBT * NST
+  long long items;  // I * NG * NBT * NST
 };
 
 void launch_pack_weights(const float* W, const float* bias, float* Wp, float* Bp, int I, int O,
@@ -134,7 +135,7 @@ cudaError_t launch_route_stream(const RouteParams& p, int T, int OPL, bool bf16,
 
 void launch_pack_weights_mma(const float* W, const float* bias, float* Wm, float* Bm, int I, int O,
                              int D, int d, int T, int OPL, int KC, int x3, cudaStream_t stream);
-size_t uhat_gemm_smem_bytes(int MT, int KC, int x3);
+size_t uhat_gemm_smem_bytes(int MTG, int KC, int x3);
 void launch_unpack_uhat(const void* u, float* out, int B, int S, int I, int O, int D, int T, int OPL,
                         int Bpad, int is_bf16, cudaStream_t stream);
 

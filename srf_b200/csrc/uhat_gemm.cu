@@ -115,7 +115,9 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = p.MT, KC = p.KC;
-  const uint32_t a_tile = (uint32_t)MT * KC * 2048u;    // one image of W[i]
+  // W[i] is resident MTG M tiles at a time (all of them unless two images would not fit)
+  const int MTG = p.MTG, NG = p.NG;
+  const uint32_t a_tile = (uint32_t)MTG * KC * 2048u;   // one image of a group of M tiles
   const uint32_t a_bytes = X3 ? 2u * a_tile : a_tile;   // hi (+ lo)
   const uint32_t x_bytes = (uint32_t)KC * UH_N * 16u;   // one x tile
 
@@ -164,20 +166,27 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int cur_i = -1;
+      int cur_ig = -1;
       uint32_t n_w = 0, n_x = 0;
       for (long long item = item_lo; item < item_hi; ++item) {
-        const int i = (int)(item / ntiles), tile = (int)(item % ntiles);
-        if (i != cur_i) {
-          ptx::mbar_wait(w_empty, (n_w & 1) ^ 1);  // previous W[i] no longer read by the MMAs
-          ptx::mbar_arrive_expect_tx(w_full, a_bytes);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wm) + (size_t)i * a_bytes;
-          for (uint32_t off = 0; off < a_bytes; off += 16384u) {
-            const uint32_t n = a_bytes - off < 16384u ? a_bytes - off : 16384u;
-            ptx::bulk_g2s(sA + off, src + off, n, w_full);
+        const int ig = (int)(item / ntiles), tile = (int)(item % ntiles);
+        const int i = ig / NG, grp = ig - i * NG;
+        if (ig != cur_ig) {
+          const int mt0 = grp * MTG, mtn = min(MTG, MT - mt0);
+          const uint32_t part = (uint32_t)mtn * KC * 2048u;       // bytes of this group's image
+          ptx::mbar_wait(w_empty, (n_w & 1) ^ 1);  // previous weights no longer read by the MMAs
+          ptx::mbar_arrive_expect_tx(w_full, X3 ? 2u * part : part);
+          for (int im = 0; im < (X3 ? 2 : 1); ++im) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wm) +
+                                 (((size_t)i * (X3 ? 2 : 1) + im) * MT + mt0) * KC * 2048u;
+            uint8_t* dst = sA + (size_t)im * a_tile;
+            for (uint32_t off = 0; off < part; off += 16384u) {
+              const uint32_t n = part - off < 16384u ? part - off : 16384u;
+              ptx::bulk_g2s(dst + off, src + off, n, w_full);
+            }
           }
           ++n_w;
-          cur_i = i;
+          cur_ig = ig;
         }
         const int st = n_x % UH_XSTAGES;
         ptx::mbar_wait(&x_empty[st], ((n_x / UH_XSTAGES) & 1) ^ 1);
@@ -194,19 +203,20 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_tf32(128, UH_N);
       const uint32_t sA_addr = ptx::smem_u32(sA), sX_addr = ptx::smem_u32(sX);
-      int cur_i = -1;
+      int cur_ig = -1;
       uint32_t n_w = 0, n_x = 0, n_t = 0;
       for (long long item = item_lo; item < item_hi; ++item) {
-        const int i = (int)(item / ntiles);
-        if (i != cur_i) {
+        const int ig = (int)(item / ntiles);
+        const int mtn = min(MTG, MT - (ig % NG) * MTG);
+        if (ig != cur_ig) {
           ptx::mbar_wait(w_full, n_w & 1);
           ++n_w;
-          cur_i = i;
+          cur_ig = ig;
         }
         const int st = n_x % UH_XSTAGES;
         ptx::mbar_wait(X3 ? &x_split[st] : &x_full[st], (n_x / UH_XSTAGES) & 1);
         ptx::tc_fence_after();
-        for (int mt = 0; mt < MT; ++mt) {
+        for (int mt = 0; mt < mtn; ++mt) {
           const int slot = n_t % UH_SLOTS;
           ptx::mbar_wait(&t_empty[slot], ((n_t / UH_SLOTS) & 1) ^ 1);
           ptx::tc_fence_after();
@@ -232,8 +242,8 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
         }
         ptx::mma_commit(&x_empty[st]);
         ++n_x;
-        const bool last_of_i = (item + 1 == item_hi) || ((int)((item + 1) / ntiles) != i);
-        if (last_of_i) ptx::mma_commit(w_empty);
+        const bool last_of_group = (item + 1 == item_hi) || ((int)((item + 1) / ntiles) != ig);
+        if (last_of_group) ptx::mma_commit(w_empty);
       }
     }
   } else if (warp >= 2 + UH_EPI_WARPS) {
@@ -274,7 +284,8 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     const long long gstride = (long long)p.I * MT * 256 * ES;  // bytes between frame pairs
     uint8_t* const ubytes = reinterpret_cast<uint8_t*>(p.u);
     for (long long item = item_lo; item < item_hi; ++item) {
-      const int i = (int)(item / ntiles), tile = (int)(item % ntiles);
+      const int ig = (int)(item / ntiles), tile = (int)(item % ntiles);
+      const int i = ig / NG, mt0 = (ig - i * NG) * MTG, mtn = min(MTG, MT - mt0);
       const int b0 = (tile % p.NBT) * p.NB, s0 = (tile / p.NBT) * p.NS;
       // byte offset of the frame pair and validity of the 16 column pairs this warp owns
       long long gofs[16];
@@ -287,7 +298,8 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
         if (s < p.S && b < p.B) okmask |= 1u << pr;
       }
       const bool all_ok = okmask == 0xffffu;
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int ml = 0; ml < mtn; ++ml) {
+        const int mt = mt0 + ml;
         const int slot = n_t % UH_SLOTS;
         const float bias = __ldg(p.Bm + ((size_t)i * MT + mt) * 128 + row);
         uint8_t* const prow = ubytes + (((size_t)i * MT + mt) * 128 + row) * 2 * ES;
@@ -339,15 +351,15 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
   }
 }
 
-size_t uhat_gemm_smem_bytes(int MT, int KC, int x3) {
+size_t uhat_gemm_smem_bytes(int MTG, int KC, int x3) {
   const size_t mul = x3 ? 2 : 1;
-  return mul * ((size_t)MT * KC * 2048 + (size_t)UH_XSTAGES * KC * UH_N * 16) +
+  return mul * ((size_t)MTG * KC * 2048 + (size_t)UH_XSTAGES * KC * UH_N * 16) +
          sizeof(uint64_t) * (3 * UH_XSTAGES + 2 * UH_SLOTS + 2) + 16;
 }
 
 cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int num_sms,
                              cudaStream_t stream) {
-  const size_t smem = uhat_gemm_smem_bytes(p.MT, p.KC, p.x3);
+  const size_t smem = uhat_gemm_smem_bytes(p.MTG, p.KC, p.x3);
   auto kern = p.x3 ? uhat_gemm_kernel<false, true>
                    : (p.store_bf16 ? uhat_gemm_kernel<true, false> : uhat_gemm_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -117,17 +117,15 @@ class LayerArgs:
 
 def exact_mode(d: int, O: int, D: int, emb_aligned: bool = True) -> str:
   """The fastest u_hat mode of the 1e-4 parity class for a layer shape: "fp32x3" (3 x TF32 split on
-  the tensor cores) where its tiles exist and fit in shared memory, else "fp32" (fused CUDA-core
-  kernel).  Mirrors uhat_geometry / uhat_gemm_smem_bytes of csrc/capi.cu, csrc/uhat_gemm.cu."""
+  the tensor cores) where its kernels are instantiated, else "fp32" (fused CUDA-core kernel).
+  Mirrors uhat_geometry / route_layer_impl of csrc/capi.cu."""
   if d % 4 != 0 or not emb_aligned or O > 128 or D > 32 or d > 32:
     return "fp32"
   T = 8 if D <= 8 else (16 if D <= 16 else (20 if D <= 20 else 32))
   OPL = 1 if O <= 32 else (2 if O <= 64 else 4)   # the kernels' output capsules per lane
   if (T == 16 and OPL > 2) or (T == 20 and OPL > 2) or (T == 32 and OPL > 1):
     return "fp32"
-  MT, KC = OPL * (T // 4), 2 * ((d + 7) // 8)
-  smem = 2 * (MT * KC * 2048 + 4 * KC * 64 * 16) + 8 * (3 * 4 + 2 * 8 + 2) + 16
-  return "fp32x3" if smem <= 227 * 1024 else "fp32"
+  return "fp32x3"   # the GEMM keeps as many M tiles of W[i] resident as fit, so every shape fits
 
 
 def _fill_desc(desc: _lib.LayerDesc, a: LayerArgs, emb, B, S, H, d, out_caps, out_logits):

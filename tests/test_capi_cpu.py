@@ -80,12 +80,13 @@ def test_product_never_imports_oracle():
 
 def test_exact_mode_picks_the_tensor_split_where_it_fits():
   """host rule of uhat_mode="exact" (the default of RoutingStack / SequenceRouter): fp32x3 when the
-  3 x TF32 GEMM has tiles for the shape and its two weight images fit in shared memory."""
+  3 x TF32 path is instantiated for the shape."""
   from srf_b200 import routing
   assert routing.exact_mode(20, 30, 20) == "fp32x3"      # WSJ-shaped
   assert routing.exact_mode(8, 63, 8) == "fp32x3"        # TIMIT-shaped last layer
   assert routing.exact_mode(6, 30, 8) == "fp32"          # d % 4 != 0
-  assert routing.exact_mode(32, 6, 32) == "fp32"         # two 128 KB images of W[i]
-  assert routing.exact_mode(20, 60, 20) == "fp32"        # O = 60, D = 20: does not fit either
+  assert routing.exact_mode(32, 6, 32) == "fp32x3"       # W[i] resident in groups of M tiles
+  assert routing.exact_mode(20, 60, 20) == "fp32x3"
+  assert routing.exact_mode(20, 100, 20) == "fp32"       # O > 64 with D > 8 is not instantiated
   assert routing.exact_mode(8, 100, 8) == "fp32x3"
   assert routing.exact_mode(20, 30, 20, emb_aligned=False) == "fp32"

@@ -257,25 +257,11 @@ TENSOR_LAYER_CASES = [
 ]
 
 
-def _x3_does_not_fit(mode, d, D):
-  """fp32x3 keeps two images of W[i] in shared memory: D = d = 32 (2 x 128 KB) does not fit and
-  is rejected with a ValueError (use fp32 there)."""
-  return mode == "fp32x3" and d > 24 and D > 24
-
-
-def test_fp32x3_rejects_tiles_that_do_not_fit():
-  emb, W, bias = _mk_layer(1, 6, 5, 32, 6, 32, 3, seed=1)
-  with pytest.raises(ValueError):
-    _run_layer(emb, W, bias, 1, 1, 1, True, False, uhat_mode="fp32x3")
-
-
 @pytest.mark.parametrize("mode", ["tf32", "bf16", "fp32x3"])
 def test_uhat_gemm_matches_oracle(mode):
   from srf_b200 import routing
   for case in TENSOR_LAYER_CASES:
     B, S, H, d, O, D, lpad, rpad = case
-    if _x3_does_not_fit(mode, d, D):
-      continue
     emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=5)
     ref = o.prediction_vectors(o.window_gather(emb.double(), lpad, rpad), W.double(), bias.double())
     out = routing.uhat_fwd(emb.cuda(), W.cuda(), bias.cuda(), lpad, rpad, mode)
@@ -289,8 +275,6 @@ def test_uhat_gemm_matches_oracle(mode):
 @pytest.mark.parametrize("mode", ["tf32", "bf16", "fp32x3"])
 def test_tensor_path_single_layer(case, sdr, mode):
   B, S, H, d, O, D, lpad, rpad = case
-  if _x3_does_not_fit(mode, d, D):
-    pytest.skip("fp32x3: W[i] hi+lo images exceed shared memory")
   emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=17)
   for iters, last in ((1, False), (3, True)):
     ref = o.route_layer(emb.double(), W.double(), bias.double(), lpad, rpad, iters, sdr, last)

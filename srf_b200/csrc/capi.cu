@@ -416,7 +416,8 @@ static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
   // M tiles of W[i] resident at a time: all of them, or as many as fit (the x tiles are then
   // streamed once per group)
   g->MTG = g->MT;
-  while (g->MTG > 1 && srf::uhat_gemm_smem_bytes(g->MTG, g->KC, g->x3 ? 1 : 0) > (size_t)h->max_smem)
+  while (g->x3 && g->MTG > 1 &&
+         srf::uhat_gemm_smem_bytes(g->MTG, g->KC, 1) > (size_t)h->max_smem)
     g->MTG = (g->MTG + 1) / 2;
   g->NG = (g->MT + g->MTG - 1) / g->MTG;
   if (srf::uhat_gemm_smem_bytes(g->MTG, g->KC, g->x3 ? 1 : 0) > (size_t)h->max_smem)

@@ -109,14 +109,17 @@ constexpr int UH_THREADS = (3 + UH_EPI_WARPS) * 32;  // + one splitter warp (3 x
 // x tile in place as x_hi = x with the 13 low mantissa bits cleared (exactly TF32-representable)
 // and writes x_lo = x - x_hi (exact) to a second buffer; the MMA issuer accumulates
 // W_hi x_hi + W_lo x_hi + W_hi x_lo in the same TMEM slot: u_hat carries fp32-class error.
-template <bool BF16, bool X3>
+// GRP: W[i] resident in groups of M tiles (only where its images exceed shared memory); the
+// common GRP = false build has NG = 1 folded at compile time (the epilogue is close to
+// instruction bound: the per-item index arithmetic of the grouped form costs it 5 %).
+template <bool BF16, bool X3, bool GRP>
 __global__ void __launch_bounds__(UH_THREADS, 1)
 uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = p.MT, KC = p.KC;
   // W[i] is resident MTG M tiles at a time (all of them unless two images would not fit)
-  const int MTG = p.MTG, NG = p.NG;
+  const int MTG = GRP ? p.MTG : MT, NG = GRP ? p.NG : 1;
   const uint32_t a_tile = (uint32_t)MTG * KC * 2048u;   // one image of a group of M tiles
   const uint32_t a_bytes = X3 ? 2u * a_tile : a_tile;   // hi (+ lo)
   const uint32_t x_bytes = (uint32_t)KC * UH_N * 16u;   // one x tile
@@ -170,7 +173,7 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
       uint32_t n_w = 0, n_x = 0;
       for (long long item = item_lo; item < item_hi; ++item) {
         const int ig = (int)(item / ntiles), tile = (int)(item % ntiles);
-        const int i = ig / NG, grp = ig - i * NG;
+        const int i = NG == 1 ? ig : ig / NG, grp = NG == 1 ? 0 : ig - i * NG;  // no division on the common path
         if (ig != cur_ig) {
           const int mt0 = grp * MTG, mtn = min(MTG, MT - mt0);
           const uint32_t part = (uint32_t)mtn * KC * 2048u;       // bytes of this group's image
@@ -207,7 +210,7 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
       uint32_t n_w = 0, n_x = 0, n_t = 0;
       for (long long item = item_lo; item < item_hi; ++item) {
         const int ig = (int)(item / ntiles);
-        const int mtn = min(MTG, MT - (ig % NG) * MTG);
+        const int mtn = NG == 1 ? MT : min(MTG, MT - (ig % NG) * MTG);
         if (ig != cur_ig) {
           ptx::mbar_wait(w_full, n_w & 1);
           ++n_w;
@@ -285,7 +288,10 @@ uhat_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const UhatParams p)
     uint8_t* const ubytes = reinterpret_cast<uint8_t*>(p.u);
     for (long long item = item_lo; item < item_hi; ++item) {
       const int ig = (int)(item / ntiles), tile = (int)(item % ntiles);
-      const int i = ig / NG, mt0 = (ig - i * NG) * MTG, mtn = min(MTG, MT - mt0);
+      // the epilogue is close to instruction bound: keep the integer divisions off the common path
+      const int i = NG == 1 ? ig : ig / NG;
+      const int mt0 = NG == 1 ? 0 : (ig - i * NG) * MTG;
+      const int mtn = NG == 1 ? MT : min(MTG, MT - mt0);
       const int b0 = (tile % p.NBT) * p.NB, s0 = (tile / p.NBT) * p.NS;
       // byte offset of the frame pair and validity of the 16 column pairs this warp owns
       long long gofs[16];
@@ -360,8 +366,10 @@ size_t uhat_gemm_smem_bytes(int MTG, int KC, int x3) {
 cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int num_sms,
                              cudaStream_t stream) {
   const size_t smem = uhat_gemm_smem_bytes(p.MTG, p.KC, p.x3);
-  auto kern = p.x3 ? uhat_gemm_kernel<false, true>
-                   : (p.store_bf16 ? uhat_gemm_kernel<true, false> : uhat_gemm_kernel<false, false>);
+  if (p.NG > 1 && !p.x3) return cudaErrorInvalidValue;  // grouped form is built for fp32x3 only
+  auto kern = p.x3 ? (p.NG > 1 ? uhat_gemm_kernel<false, true, true> : uhat_gemm_kernel<false, true, false>)
+                   : (p.store_bf16 ? uhat_gemm_kernel<true, false, false>
+                                   : uhat_gemm_kernel<false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long grid = p.items < num_sms ? p.items : num_sms;

@@ -51,6 +51,17 @@ struct srf_handle {
   void* ubuf = nullptr;  // materialised u_hat of one layer
   size_t ubuf_bytes = 0;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled
+  // fused routing kernel (routing_fused.cu)
+  std::vector<PackedWeights> packed_fused;
+  int no_fused = 0;
+  void* fz_tab = nullptr;        // device: FusedLayer[] + FusedItem[] + counters + progress
+  size_t fz_tab_bytes = 0;
+  float* fz_x = nullptr;         // device: exchange buffers (partial sums, squashed outputs)
+  size_t fz_x_bytes = 0;
+  std::vector<float*> fz_inter;  // inter-layer capsule buffers of a wavefront launch
+  size_t fz_inter_bytes = 0;
+  int* fz_host_abort = nullptr;  // mapped host word: abort code of a timed-out fused launch
+  int* fz_host_abort_dev = nullptr;
   // per-kernel timing (srf_profile_begin/end)
   bool profiling = false;
   struct Span {
@@ -142,6 +153,15 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_NO_STREAM")) h->no_stream = atoi(s);
   if (const char* s = getenv("SRF_STREAM_STAGES")) h->max_stages = atoi(s);
   if (const char* s = getenv("SRF_BWD_ATOMICS")) h->bwd_atomics = atoi(s);
+  if (const char* s = getenv("SRF_NO_FUSED")) h->no_fused = atoi(s);
+  if (cudaHostAlloc((void**)&h->fz_host_abort, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    *h->fz_host_abort = 0;
+    if (cudaHostGetDevicePointer((void**)&h->fz_host_abort_dev, h->fz_host_abort, 0) != cudaSuccess)
+      h->fz_host_abort_dev = nullptr;
+  } else {
+    cudaGetLastError();
+    h->fz_host_abort = nullptr;
+  }
   if (const char* s = getenv("SRF_PHASE_TIMERS")) {
     if (atoi(s) > 0 && cudaMalloc((void**)&h->dbg, 1024 * 8 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(h->dbg, 0, 1024 * 8 * sizeof(unsigned long long));
@@ -160,6 +180,14 @@ extern "C" int srf_destroy(srf_handle* h) {
     if (pw.Wp) cudaFree(pw.Wp);
   }
   if (h->ubuf) cudaFree(h->ubuf);
+  for (auto& pw : h->packed_fused) {
+    if (pw.Wp) cudaFree(pw.Wp);
+  }
+  if (h->fz_tab) cudaFree(h->fz_tab);
+  if (h->fz_x) cudaFree(h->fz_x);
+  for (float* b : h->fz_inter)
+    if (b) cudaFree(b);
+  if (h->fz_host_abort) cudaFreeHost(h->fz_host_abort);
   if (h->dbg) cudaFree(h->dbg);
   if (h->ctc_ws) cudaFree(h->ctc_ws);
   if (h->bwd_ws) cudaFree(h->bwd_ws);
@@ -282,6 +310,14 @@ extern "C" int64_t srf_launch_count(const srf_handle* h) { return h ? h->launche
 
 extern "C" const char* srf_last_kernel(const srf_handle* h) {
   return h ? h->last_kernel.c_str() : "";
+}
+
+// the checks of validate_layer that decide eligibility for a fused stack, without an error message
+static bool validate_layer_quiet(const srf_layer_desc* L, bool need_emb) {
+  if (!L || !L->W || !L->bias || (need_emb && !L->emb)) return false;
+  if (L->B < 0 || L->S < 0 || L->H <= 0 || L->d <= 0 || L->O <= 0 || L->D <= 0) return false;
+  if (L->lpad < 0 || L->rpad < 0 || L->iters < 1) return false;
+  return true;
 }
 
 static int validate_layer(srf_handle* h, const srf_layer_desc* L, bool fwd = true) {
@@ -574,6 +610,378 @@ extern "C" int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* L, float* out_u
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// fused routing kernel (routing_fused.cu): eligibility, packed operand images, work plan, launch
+// ---------------------------------------------------------------------------------------
+namespace {
+struct FusedGeom {
+  int T4, opl, KC, KX, I;
+};
+}  // namespace
+
+// a previous fused launch that timed out left its code in the mapped host word
+static int fused_check_abort(srf_handle* h) {
+  if (h->fz_host_abort && *h->fz_host_abort != 0) {
+    const int code = *h->fz_host_abort;
+    *h->fz_host_abort = 0;
+    return fail(h, 700 + code, "a fused routing launch timed out waiting (wait site %d); its results are invalid", code);
+  }
+  return 0;
+}
+
+static bool fused_geometry(const srf_handle* h, const srf_layer_desc* L, FusedGeom* g) {
+  if (h->no_fused) return false;
+  if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_FP32X3) return false;
+  if (L->d % 4 != 0 || L->d > 32 || L->D > 20 || L->O > 64 || L->iters > 64) return false;
+  if (L->emb && (reinterpret_cast<uintptr_t>(L->emb) & 15) != 0) return false;
+  const int t4 = (L->D + 3) / 4;
+  g->T4 = t4 <= 2 ? 2 : (t4 <= 4 ? 4 : 5);
+  g->opl = (L->O + 31) / 32;
+  if (!srf::route_fused_supported(g->T4, g->opl)) return false;
+  g->KX = L->d / 4;
+  g->KC = 2 * ((L->d + 1 + 7) / 8);
+  g->I = (L->lpad + L->rpad + 1) * L->H;
+  return true;
+}
+
+static int get_packed_fused(srf_handle* h, const srf_layer_desc* L, const FusedGeom& g, int T4, int parts,
+                            cudaStream_t stream, const PackedWeights** out) {
+  PackedWeights* hit = nullptr;
+  for (auto& pw : h->packed_fused)
+    if (pw.W == L->W && pw.bias == L->bias && pw.x3 == parts && pw.T == T4) {
+      hit = &pw;
+      break;
+    }
+  const size_t nW = (size_t)g.I * parts * g.opl * T4 * g.KC * 512;
+  const size_t bytes = nW * sizeof(float);
+  const bool same = hit && hit->I == g.I && hit->O == L->O && hit->D == L->D && hit->d == L->d;
+  if (same && L->weights_version != 0 && hit->version == L->weights_version) {
+    *out = hit;
+    return 0;
+  }
+  if (!hit) {
+    if (h->packed_fused.size() >= 64) {
+      for (auto& pw : h->packed_fused)
+        if (pw.Wp) cudaFreeAsync(pw.Wp, stream);
+      h->packed_fused.clear();
+    }
+    h->packed_fused.emplace_back();
+    hit = &h->packed_fused.back();
+  }
+  if (hit->bytes < bytes) {
+    if (hit->Wp) cudaFreeAsync(hit->Wp, stream);
+    hit->Wp = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&hit->Wp, bytes, stream);
+    if (e != cudaSuccess) {
+      hit->bytes = 0;
+      return cuda_fail(h, e, "packed fused weight allocation");
+    }
+    hit->bytes = bytes;
+  }
+  hit->W = L->W;
+  hit->bias = L->bias;
+  hit->I = g.I;
+  hit->O = L->O;
+  hit->D = L->D;
+  hit->d = L->d;
+  hit->T = T4;
+  hit->version = L->weights_version;
+  hit->x3 = parts;
+  {
+    KernelSpan span(h, 0, stream);
+    srf::launch_pack_weights_fused(L->W, L->bias, hit->Wp, g.I, L->O, L->D, L->d, T4, g.opl, g.KC, parts,
+                                   stream);
+  }
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, "pack_weights_fused launch");
+  *out = hit;
+  return 0;
+}
+
+static int fused_tensor_map(srf_handle* h, const float* emb, int B, int S, int H, int d, int NB, int NS,
+                            CUtensorMap* tmap) {
+  if (!h->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+      return fail(h, e != cudaSuccess ? (int)e : 999, "cuTensorMapEncodeTiled is not available");
+    h->encode_tiled = fn;
+  }
+  // emb[B,S,H,d] viewed as 5-D (4 floats, b, s, h, d/4); box (4, NB, NS, 1, d/4) lands in shared
+  // memory as [K chunk][s][b][4 floats] = K-major UMMA operand; out-of-bounds -> zeros
+  const cuuint64_t gdim[5] = {4, (cuuint64_t)B, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)(d / 4)};
+  const cuuint64_t gstr[4] = {(cuuint64_t)S * H * d * 4, (cuuint64_t)H * d * 4, (cuuint64_t)d * 4, 16};
+  const cuuint32_t box[5] = {4, (cuuint32_t)NB, (cuuint32_t)NS, 1, (cuuint32_t)(d / 4)};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = ((EncodeTiledFn)h->encode_tiled)(
+      tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(emb), gdim, gstr, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS)
+    return fail(h, 900 + (int)cr, "cuTensorMapEncodeTiled failed (CUresult %d; B=%d S=%d H=%d d=%d box %dx%d)",
+                (int)cr, B, S, H, d, NB, NS);
+  return 0;
+}
+
+// One fused launch: an SDR stack of n layers as a wavefront, or ONE DR layer (n == 1).
+// `layers` are validated, all fused-eligible, and agree on B, S, sdr, iters and uhat_mode.
+static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cudaStream_t stream) {
+  int rc = fused_check_abort(h);
+  if (rc) return rc;
+  const srf_layer_desc& L0 = layers[0];
+  const int B = L0.B, S = L0.S, sdr = L0.sdr ? 1 : 0;
+  const int parts = L0.uhat_mode == SRF_UHAT_FP32X3 ? 2 : 1;
+  std::vector<FusedGeom> geo(n);
+  int T4 = 0, OPLM = 0, KCmax = 0;
+  for (int l = 0; l < n; ++l) {
+    if (!fused_geometry(h, &layers[l], &geo[l])) return fail(h, -3, "layer %d is not fused-eligible", l);
+    if (geo[l].T4 > T4) T4 = geo[l].T4;
+    if (geo[l].opl > OPLM) OPLM = geo[l].opl;
+    if (geo[l].KC > KCmax) KCmax = geo[l].KC;
+  }
+  if (!srf::route_fused_supported(T4, OPLM)) return fail(h, -3, "fused variant T4=%d OPL=%d not built", T4, OPLM);
+  const int T = 4 * T4, OP = 32 * OPLM;
+
+  // ---- work plan ----
+  int NB = 32, NS = 1, ngroups, grid, rounds, nslots, maxC = 1;
+  std::vector<int> Cl(n, 1);
+  int Gc = 1, NBT = 1;
+  if (sdr) {
+    ngroups = (B + 31) / 32;
+    Gc = h->num_sms / n;
+    if (Gc < 1) return fail(h, -3, "more layers than SMs");
+    if (Gc > ngroups) Gc = ngroups;
+    rounds = (ngroups + Gc - 1) / Gc;
+    int budget = h->num_sms / Gc - n;  // CTAs to hand out on top of one per layer
+    while (budget > 0) {
+      int best = -1;
+      double worst = 0.0;
+      for (int l = 0; l < n; ++l) {
+        if (Cl[l] >= geo[l].I) continue;
+        const double load = (double)geo[l].I / Cl[l];
+        if (load > worst) {
+          worst = load;
+          best = l;
+        }
+      }
+      if (best < 0) break;
+      Cl[best]++;
+      budget--;
+    }
+    if (h->force_C > 0)
+      for (int l = 0; l < n; ++l) Cl[l] = h->force_C < geo[l].I ? h->force_C : geo[l].I;
+    int per_group = 0;
+    for (int l = 0; l < n; ++l) {
+      per_group += Cl[l];
+      if (Cl[l] > maxC) maxC = Cl[l];
+    }
+    if (per_group * Gc > h->num_sms) return fail(h, -3, "fused plan exceeds the SM count");
+    grid = per_group * Gc;
+    nslots = Gc * n;
+  } else {
+    NB = 1;
+    while (NB < 32 && NB < B) NB *= 2;
+    NS = 32 / NB;
+    NBT = (B + NB - 1) / NB;
+    const int NST = (S + NS - 1) / NS;
+    ngroups = NBT * NST;
+    if (ngroups >= h->num_sms) {
+      grid = h->num_sms;
+      rounds = (ngroups + grid - 1) / grid;
+      nslots = grid;
+    } else {
+      int C = h->num_sms / ngroups;
+      if (C > geo[0].I) C = geo[0].I;
+      if (h->force_C > 0 && h->force_C <= C) C = h->force_C;
+      Cl[0] = maxC = C;
+      grid = ngroups * C;
+      rounds = 1;
+      nslots = ngroups;
+    }
+  }
+  std::vector<srf::FusedItem> items((size_t)rounds * grid);
+  for (auto& itm : items) itm.layer = -1;
+  auto vmask_of = [&](int b0, int s0) {
+    unsigned m = 0;
+    for (int f = 0; f < 32; ++f)
+      if (b0 + f % NB < B && s0 + f / NB < S) m |= 1u << f;
+    return m;
+  };
+  if (sdr) {
+    for (int r = 0; r < rounds; ++r) {
+      int cta = 0;
+      for (int gs = 0; gs < Gc; ++gs)
+        for (int l = 0; l < n; ++l)
+          for (int c = 0; c < Cl[l]; ++c, ++cta) {
+            const int group = r * Gc + gs;
+            if (group >= ngroups) continue;
+            srf::FusedItem& itm = items[(size_t)r * grid + cta];
+            itm.layer = l;
+            itm.group = group;
+            itm.slot = gs * n + l;
+            itm.c = c;
+            itm.C = Cl[l];
+            itm.i_lo = (int)((long long)geo[l].I * c / Cl[l]);
+            itm.i_hi = (int)((long long)geo[l].I * (c + 1) / Cl[l]);
+            itm.b0 = group * 32;
+            itm.s0 = 0;
+            itm.vmask = vmask_of(itm.b0, 0);
+          }
+    }
+  } else {
+    const int C = Cl[0];
+    for (int r = 0; r < rounds; ++r)
+      for (int cta = 0; cta < grid; ++cta) {
+        const int group = C > 1 ? cta / C : r * grid + cta;
+        if (group >= ngroups) continue;
+        srf::FusedItem& itm = items[(size_t)r * grid + cta];
+        itm.layer = 0;
+        itm.group = group;
+        itm.slot = C > 1 ? group : cta;
+        itm.c = C > 1 ? cta % C : 0;
+        itm.C = C;
+        itm.i_lo = (int)((long long)geo[0].I * itm.c / C);
+        itm.i_hi = (int)((long long)geo[0].I * (itm.c + 1) / C);
+        itm.b0 = (group % NBT) * NB;
+        itm.s0 = (group / NBT) * NS;
+        itm.vmask = vmask_of(itm.b0, itm.s0);
+      }
+  }
+
+  // ---- inter-layer buffers, packed weights, device descriptors ----
+  std::vector<srf::FusedLayer> fl(n);
+  memset(fl.data(), 0, sizeof(srf::FusedLayer) * n);
+  const float* prev_out = nullptr;
+  for (int l = 0; l < n; ++l) {
+    const srf_layer_desc& L = layers[l];
+    const bool is_final = l == n - 1;
+    float* out_caps = L.out_caps;
+    if (!out_caps && !(is_final && L.head_gamma)) {
+      const size_t bytes = (size_t)B * S * L.O * L.D * sizeof(float);
+      if ((int)h->fz_inter.size() < n) h->fz_inter.resize(n, nullptr);
+      if (bytes > h->fz_inter_bytes) {
+        for (float*& b : h->fz_inter) {
+          if (b) cudaFreeAsync(b, stream);
+          b = nullptr;
+        }
+        h->fz_inter_bytes = bytes;
+      }
+      if (!h->fz_inter[l]) {
+        cudaError_t e = cudaMallocAsync((void**)&h->fz_inter[l], h->fz_inter_bytes, stream);
+        if (e != cudaSuccess) return cuda_fail(h, e, "inter-layer buffer allocation");
+      }
+      out_caps = h->fz_inter[l];
+    }
+    const float* emb = L.emb ? L.emb : prev_out;
+    if (!emb) return fail(h, -1, "layer %d: emb is NULL", l);
+    if ((reinterpret_cast<uintptr_t>(emb) & 15) != 0) return fail(h, -3, "layer %d: emb is not 16-byte aligned", l);
+    const PackedWeights* pw = nullptr;
+    rc = get_packed_fused(h, &L, geo[l], T4, parts, stream, &pw);
+    if (rc) return rc;
+    srf::FusedLayer& F = fl[l];
+    rc = fused_tensor_map(h, emb, B, S, L.H, L.d, NB, NS, &F.tmap);
+    if (rc) return rc;
+    F.Wf = pw->Wp;
+    F.ln_gamma = L.ln_gamma;
+    F.ln_beta = L.ln_beta;
+    F.dropout_mask = L.dropout_mask;
+    F.head_gamma = L.head_gamma;
+    F.head_beta = L.head_beta;
+    F.out_caps = out_caps;
+    F.out_logits = L.out_logits;
+    F.out_raw = L.out_raw;
+    F.H = L.H;
+    F.O = L.O;
+    F.D = L.D;
+    F.opl = geo[l].opl;
+    F.KC = geo[l].KC;
+    F.KX = geo[l].KX;
+    F.lpad = L.lpad;
+    F.rpad = L.rpad;
+    F.mask0 = L.mask_class0 ? 1 : 0;
+    F.dep_layer = (l > 0 && emb == prev_out) ? l - 1 : -1;
+    F.ln_eps = L.ln_eps;
+    F.length_eps = L.length_eps;
+    prev_out = out_caps;
+  }
+
+  // device table: layers | items | cnt_p | cnt_v | progress | abort
+  const size_t off_items = sizeof(srf::FusedLayer) * n;
+  const size_t off_cnt = (off_items + sizeof(srf::FusedItem) * items.size() + 63) & ~(size_t)63;
+  const size_t n_prog = sdr ? (size_t)n * ngroups * 32 : 0;
+  const size_t cnt_ints = (size_t)nslots * 3 + n_prog + 16;
+  const size_t tab_bytes = off_cnt + cnt_ints * sizeof(int);
+  if (tab_bytes > h->fz_tab_bytes) {
+    if (h->fz_tab) cudaFreeAsync(h->fz_tab, stream);
+    h->fz_tab = nullptr;
+    h->fz_tab_bytes = 0;
+    cudaError_t e = cudaMallocAsync(&h->fz_tab, tab_bytes, stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "fused table allocation");
+    h->fz_tab_bytes = tab_bytes;
+  }
+  const size_t x_floats = (size_t)nslots * (maxC + 1) * 32 * T * OP;
+  if (x_floats * sizeof(float) > h->fz_x_bytes) {
+    if (h->fz_x) cudaFreeAsync(h->fz_x, stream);
+    h->fz_x = nullptr;
+    h->fz_x_bytes = 0;
+    cudaError_t e = cudaMallocAsync((void**)&h->fz_x, x_floats * sizeof(float), stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "fused exchange buffer allocation");
+    h->fz_x_bytes = x_floats * sizeof(float);
+  }
+  uint8_t* tab = reinterpret_cast<uint8_t*>(h->fz_tab);
+  // pageable source: the runtime stages the bytes before returning, the vectors may die after this
+  cudaError_t e = cudaMemcpyAsync(tab, fl.data(), sizeof(srf::FusedLayer) * n, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(tab + off_items, items.data(), sizeof(srf::FusedItem) * items.size(),
+                        cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(tab + off_cnt, 0, cnt_ints * sizeof(int), stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "fused table upload");
+
+  srf::FusedParams p;
+  p.layers = reinterpret_cast<const srf::FusedLayer*>(tab);
+  p.items = reinterpret_cast<const srf::FusedItem*>(tab + off_items);
+  p.rounds = rounds;
+  int* ints = reinterpret_cast<int*>(tab + off_cnt);
+  p.cnt_p = ints;
+  p.cnt_v = ints + nslots;
+  p.progress = sdr && n > 1 ? ints + 3 * (size_t)nslots : nullptr;
+  p.abort_flag = ints + 3 * (size_t)nslots + n_prog;
+  p.host_abort = h->fz_host_abort_dev;
+  p.xP = h->fz_x;
+  p.xV = h->fz_x + (size_t)nslots * maxC * 32 * T * OP;
+  p.maxC = maxC;
+  p.ngroups = ngroups;
+  p.B = B;
+  p.S = S;
+  p.sdr = sdr;
+  p.iters = L0.iters;
+  p.NB = NB;
+  // W-tile ring: as many stages as fit beside the x ring and the exchange rows
+  int nwst = 24;
+  while (nwst > 2 && srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst) > (size_t)h->max_smem) --nwst;
+  const size_t smem = srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst);
+  if (smem > (size_t)h->max_smem) return fail(h, -3, "fused kernel does not fit in shared memory");
+  p.nwst = nwst;
+  {
+    KernelSpan span(h, 2, stream);
+    e = srf::launch_route_fused(p, T4, OPLM, parts == 2, grid, smem, stream);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return cuda_fail(h, e, "route_fused launch");
+  }
+  h->launches++;
+  char nm[240];
+  snprintf(nm, sizeof(nm),
+           "route_fused_kernel<T4=%d,OPL=%d,%s> %s layers=%d grid=%d groups=%d rounds=%d maxC=%d wstages=%d smem=%zu",
+           T4, OPLM, parts == 2 ? "3xTF32" : "tf32", sdr ? "SDR-wavefront" : "DR", n, grid, ngroups, rounds,
+           maxC, nwst, smem);
+  h->last_kernel = nm;
+  return 0;
+}
+
 static int pow2_floor(int v) {
   int p = 1;
   while (p * 2 <= v) p *= 2;
@@ -586,6 +994,10 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
   if (rc) return rc;
   if (!L->out_caps && !L->out_logits && !L->out_raw) return fail(h, -1, "no output requested");
 
+  {
+    FusedGeom fg;
+    if (fused_geometry(h, L, &fg)) return fused_forward(h, L, 1, stream);
+  }
   const int window = L->lpad + L->rpad + 1;
   const int I = window * L->H;
   const int um = L->uhat_mode == SRF_UHAT_FP32 ? 0 : (L->uhat_mode == SRF_UHAT_BF16 ? 1 : 2);
@@ -921,6 +1333,27 @@ extern "C" int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, 
     if (needs_ws) {
       const size_t bytes = (size_t)B * S * L.O * L.D * sizeof(float);
       if (bytes > need) need = bytes;
+    }
+  }
+  // SDR stacks whose layers all qualify run as ONE wavefront launch of the fused kernel
+  if (layers[0].sdr && n_layers >= 1) {
+    bool all = true;
+    for (int n = 0; n < n_layers && all; ++n) {
+      FusedGeom fg;
+      const srf_layer_desc& L = layers[n];
+      all = validate_layer_quiet(&L, n == 0) && fused_geometry(h, &L, &fg) && L.sdr &&
+            L.iters == layers[0].iters && L.uhat_mode == layers[0].uhat_mode &&
+            (L.out_caps || L.out_logits || L.out_raw || n < n_layers - 1);
+    }
+    if (all) {
+      for (int n = 0; n < n_layers; ++n) {
+        srf_layer_desc L = layers[n];
+        if (n > 0 && !L.emb) L.emb = layers[0].emb;  // placeholder for the validator only
+        int rc = validate_layer(h, &L);
+        if (rc) return rc;
+      }
+      if (B == 0 || S == 0) return 0;
+      return fused_forward(h, layers, n_layers, stream);
     }
   }
   if (need > h->ws_bytes) {

@@ -139,6 +139,12 @@ size_t uhat_gemm_smem_bytes(int MTG, int KC, int x3);
 void launch_unpack_uhat(const void* u, float* out, int B, int S, int I, int O, int D, int T, int OPL,
                         int Bpad, int is_bf16, cudaStream_t stream);
 
+// fused routing kernel (routing_fused.cu): packed operand images of W (+ bias in the K padding)
+void launch_pack_weights_fused(const float* W, const float* bias, float* Wf, int I, int O, int D, int d,
+                               int T4, int OPL, int KC, int parts, cudaStream_t stream);
+bool route_fused_supported(int T4, int OPL);
+size_t route_fused_smem_bytes(int OPL, int KC, int x3, int nwst);
+
 }  // namespace srf
 
 // needs <cuda.h> for CUtensorMap; declared separately so plain users of this header need not include it
@@ -146,5 +152,50 @@ void launch_unpack_uhat(const void* u, float* out, int B, int S, int I, int O, i
 namespace srf {
 cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int num_sms,
                              cudaStream_t stream);
+
+// ---- fused routing kernel: device-side descriptors ----
+struct alignas(64) FusedLayer {
+  CUtensorMap tmap;           // 5-D map over this layer's input capsules [B,S,H,d]
+  const float* Wf;            // [i][part][m][KC][128][4]
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* dropout_mask;
+  const float* head_gamma;
+  const float* head_beta;
+  float* out_caps;
+  float* out_logits;
+  float* out_raw;
+  int H, O, D, opl;           // opl = blocks of 32 output capsules this layer uses
+  int KC, KX;                 // 16-byte K chunks per operand row (incl. bias column) / fetched by TMA
+  int lpad, rpad, mask0;
+  int dep_layer;              // layer whose stored frames this one reads (SDR wavefront), -1 = none
+  float ln_eps, length_eps;
+};
+// one unit of work of one CTA: group `group` of layer `layer`, input capsules [i_lo, i_hi)
+struct FusedItem {
+  int layer;                  // -1 = idle
+  int group, slot;            // frame group; exchange-buffer / counter slot shared by the C CTAs
+  int c, C;
+  int i_lo, i_hi;
+  int b0, s0;                 // first utterance / time step of the group's frame tile
+  unsigned vmask;             // bit f: frame f of the tile exists
+};
+struct FusedParams {
+  const FusedLayer* layers;
+  const FusedItem* items;     // [rounds][grid]
+  int rounds;
+  float* xP;                  // [slot][maxC][32][T][OP] partial sums
+  float* xV;                  // [slot][32][T][OP]       squashed outputs
+  int* cnt_p;                 // [slot]
+  int* cnt_v;                 // [slot][2]
+  int* progress;              // [layer][group][32] frames stored (SDR wavefront), or null
+  int* abort_flag;
+  int* host_abort;            // mapped host copy of the abort code
+  int maxC, ngroups;
+  int B, S, sdr, iters, NB;
+  int nwst;                   // W-tile ring stages
+};
+cudaError_t launch_route_fused(const FusedParams& p, int T4, int OPL, int x3, int grid, size_t smem,
+                               cudaStream_t stream);
 }
 #endif

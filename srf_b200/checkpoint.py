@@ -77,6 +77,13 @@ def load_state_dict(model, state: Dict[str, np.ndarray], variant: Optional[str] 
   `expect_partial()` corresponds to strict=False)."""
   import torch
   loaded = []
+  # a freshly built SequenceRouter creates its front-end parameters lazily (first call, like the
+  # Keras layers of the reference); tf.train.Checkpoint defers the restore until then
+  # (misc_helper.py:140-163) -- here the checkpoint's front-end arrays create them right away
+  fe_state = {k[len("frontend/"):]: v for k, v in state.items() if k.startswith("frontend/")}
+  if fe_state and hasattr(model, "load_frontend") and not getattr(model, "fe", None):
+    model.load_frontend(fe_state)
+    loaded.extend("frontend/" + k for k in fe_state)
   named = dict(model.named_parameters())
   pending_w, pending_b = {}, {}
   for name, arr in state.items():
@@ -108,6 +115,11 @@ def load_state_dict(model, state: Dict[str, np.ndarray], variant: Optional[str] 
     missing = sorted(set(named) - set(loaded))
     if missing:
       raise KeyError("checkpoint is missing %s" % ", ".join(missing))
+    consumed = set(loaded)
+    for name in state:
+      base = name.rsplit("/", 1)[-1]
+      if name not in consumed and base not in consumed:
+        raise KeyError("checkpoint entry %s has no counterpart in the model" % name)
   if hasattr(model, "mark_weights_changed"):
     model.mark_weights_changed()
   elif hasattr(model, "stack"):

@@ -629,6 +629,9 @@ static int fused_check_abort(srf_handle* h) {
   return 0;
 }
 
+// fused_forward's answer for a shape it does not take: the caller runs the two-kernel path
+enum { FUSED_FALLBACK = 1 << 20 };
+
 static bool fused_geometry(const srf_handle* h, const srf_layer_desc* L, FusedGeom* g) {
   if (h->no_fused) return false;
   if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_FP32X3) return false;
@@ -699,32 +702,6 @@ static int get_packed_fused(srf_handle* h, const srf_layer_desc* L, const FusedG
   return 0;
 }
 
-static int fused_tensor_map(srf_handle* h, const float* emb, int B, int S, int H, int d, int NB, int NS,
-                            CUtensorMap* tmap) {
-  if (!h->encode_tiled) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
-      return fail(h, e != cudaSuccess ? (int)e : 999, "cuTensorMapEncodeTiled is not available");
-    h->encode_tiled = fn;
-  }
-  // emb[B,S,H,d] viewed as 5-D (4 floats, b, s, h, d/4); box (4, NB, NS, 1, d/4) lands in shared
-  // memory as [K chunk][s][b][4 floats] = K-major UMMA operand; out-of-bounds -> zeros
-  const cuuint64_t gdim[5] = {4, (cuuint64_t)B, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)(d / 4)};
-  const cuuint64_t gstr[4] = {(cuuint64_t)S * H * d * 4, (cuuint64_t)H * d * 4, (cuuint64_t)d * 4, 16};
-  const cuuint32_t box[5] = {4, (cuuint32_t)NB, (cuuint32_t)NS, 1, (cuuint32_t)(d / 4)};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult cr = ((EncodeTiledFn)h->encode_tiled)(
-      tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(emb), gdim, gstr, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS)
-    return fail(h, 900 + (int)cr, "cuTensorMapEncodeTiled failed (CUresult %d; B=%d S=%d H=%d d=%d box %dx%d)",
-                (int)cr, B, S, H, d, NB, NS);
-  return 0;
-}
-
 // One fused launch: an SDR stack of n layers as a wavefront, or ONE DR layer (n == 1).
 // `layers` are validated, all fused-eligible, and agree on B, S, sdr, iters and uhat_mode.
 static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cudaStream_t stream) {
@@ -742,6 +719,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
     if (geo[l].KC > KCmax) KCmax = geo[l].KC;
   }
   if (!srf::route_fused_supported(T4, OPLM)) return fail(h, -3, "fused variant T4=%d OPL=%d not built", T4, OPLM);
+  if (n > srf::FZ_MAX_LAYERS) return fail(h, -3, "fused launch holds at most %d layers", srf::FZ_MAX_LAYERS);
   const int T = 4 * T4, OP = 32 * OPLM;
 
   // ---- work plan ----
@@ -881,8 +859,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
     rc = get_packed_fused(h, &L, geo[l], T4, parts, stream, &pw);
     if (rc) return rc;
     srf::FusedLayer& F = fl[l];
-    rc = fused_tensor_map(h, emb, B, S, L.H, L.d, NB, NS, &F.tmap);
-    if (rc) return rc;
+    F.emb = emb;
     F.Wf = pw->Wp;
     F.ln_gamma = L.ln_gamma;
     F.ln_beta = L.ln_beta;
@@ -911,7 +888,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   const size_t off_items = sizeof(srf::FusedLayer) * n;
   const size_t off_cnt = (off_items + sizeof(srf::FusedItem) * items.size() + 63) & ~(size_t)63;
   const size_t n_prog = sdr ? (size_t)n * ngroups * 32 : 0;
-  const size_t cnt_ints = (size_t)nslots * 3 + n_prog + 16;
+  const size_t cnt_ints = (size_t)nslots * (3 + 32) + n_prog + 16;
   const size_t tab_bytes = off_cnt + cnt_ints * sizeof(int);
   if (tab_bytes > h->fz_tab_bytes) {
     if (h->fz_tab) cudaFreeAsync(h->fz_tab, stream);
@@ -946,8 +923,9 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   int* ints = reinterpret_cast<int*>(tab + off_cnt);
   p.cnt_p = ints;
   p.cnt_v = ints + nslots;
-  p.progress = sdr && n > 1 ? ints + 3 * (size_t)nslots : nullptr;
-  p.abort_flag = ints + 3 * (size_t)nslots + n_prog;
+  p.oflag = ints + 3 * (size_t)nslots;
+  p.progress = sdr && n > 1 ? ints + 35 * (size_t)nslots : nullptr;
+  p.abort_flag = ints + 35 * (size_t)nslots + n_prog;
   p.host_abort = h->fz_host_abort_dev;
   p.xP = h->fz_x;
   p.xV = h->fz_x + (size_t)nslots * maxC * 32 * T * OP;
@@ -958,12 +936,40 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   p.sdr = sdr;
   p.iters = L0.iters;
   p.NB = NB;
-  // W-tile ring: as many stages as fit beside the x ring and the exchange rows
-  int nwst = 24;
-  while (nwst > 2 && srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst) > (size_t)h->max_smem) --nwst;
-  const size_t smem = srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst);
-  if (smem > (size_t)h->max_smem) return fail(h, -3, "fused kernel does not fit in shared memory");
+  // W ring: a stage is G consecutive tiles fetched by ONE bulk copy (the copy rate is set by the
+  // bytes issued per barrier round trip: single 12 KB copies reach 19 B/clk/SM, 48 KB copies 70,
+  // profiles/r2_ubench.txt); at least 3 stages, G as large as fits up to ~48 KB
+  const size_t wpair = (size_t)KCmax * 2048 * parts;
+  int G = (int)(49152 / wpair);
+  if (G < 1) G = 1;
+  int nwst = 0;
+  for (; G >= 1; --G) {
+    nwst = 8;
+    while (nwst > 3 && srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst, G * wpair) > (size_t)h->max_smem) --nwst;
+    if (srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst, G * wpair) <= (size_t)h->max_smem) break;
+  }
+  // the MMA issuers address a capsule's tiles through at most three ring stages
+  if (G < 1 || T4 * OPLM >= 2 * G + 2) return FUSED_FALLBACK;   // the two-kernel path takes this shape
+  const size_t smem = srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst, G * wpair);
+  p.gtiles = G;
+  p.wstage_bytes = (int)(G * wpair);
+  p.xtile_bytes = KCmax * 32 * 16;
   p.nwst = nwst;
+  p.dbg = h->dbg;
+  p.n_layers = n;
+  p.per_group = 0;
+  for (int l = 0; l < srf::FZ_MAX_LAYERS; ++l) {
+    if (l < n) {
+      p.per_group += sdr ? Cl[l] : Cl[0];
+      p.layer_I[l] = geo[l].I;
+      p.layer_opl[l] = geo[l].opl;
+      p.layer_KC[l] = geo[l].KC;
+      p.layer_KX[l] = geo[l].KX;
+    } else {
+      p.layer_I[l] = p.layer_opl[l] = p.layer_KC[l] = p.layer_KX[l] = 0;
+    }
+    p.cta_end[l] = p.per_group;
+  }
   {
     KernelSpan span(h, 2, stream);
     e = srf::launch_route_fused(p, T4, OPLM, parts == 2, grid, smem, stream);
@@ -975,9 +981,10 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   h->launches++;
   char nm[240];
   snprintf(nm, sizeof(nm),
-           "route_fused_kernel<T4=%d,OPL=%d,%s> %s layers=%d grid=%d groups=%d rounds=%d maxC=%d wstages=%d smem=%zu",
+           "route_fused_kernel<T4=%d,OPL=%d,%s> %s layers=%d grid=%d groups=%d rounds=%d maxC=%d wstages=%dx%d "
+           "tiles smem=%zu",
            T4, OPLM, parts == 2 ? "3xTF32" : "tf32", sdr ? "SDR-wavefront" : "DR", n, grid, ngroups, rounds,
-           maxC, nwst, smem);
+           maxC, nwst, G, smem);
   h->last_kernel = nm;
   return 0;
 }
@@ -996,7 +1003,10 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
 
   {
     FusedGeom fg;
-    if (fused_geometry(h, L, &fg)) return fused_forward(h, L, 1, stream);
+    if (fused_geometry(h, L, &fg)) {
+      const int frc = fused_forward(h, L, 1, stream);
+      if (frc != FUSED_FALLBACK) return frc;
+    }
   }
   const int window = L->lpad + L->rpad + 1;
   const int I = window * L->H;
@@ -1336,7 +1346,7 @@ extern "C" int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, 
     }
   }
   // SDR stacks whose layers all qualify run as ONE wavefront launch of the fused kernel
-  if (layers[0].sdr && n_layers >= 1) {
+  if (layers[0].sdr && n_layers >= 1 && n_layers <= srf::FZ_MAX_LAYERS) {
     bool all = true;
     for (int n = 0; n < n_layers && all; ++n) {
       FusedGeom fg;
@@ -1353,7 +1363,8 @@ extern "C" int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, 
         if (rc) return rc;
       }
       if (B == 0 || S == 0) return 0;
-      return fused_forward(h, layers, n_layers, stream);
+      const int frc = fused_forward(h, layers, n_layers, stream);
+      if (frc != FUSED_FALLBACK) return frc;
     }
   }
   if (need > h->ws_bytes) {

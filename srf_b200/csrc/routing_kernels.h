@@ -143,7 +143,7 @@ void launch_unpack_uhat(const void* u, float* out, int B, int S, int I, int O, i
 void launch_pack_weights_fused(const float* W, const float* bias, float* Wf, int I, int O, int D, int d,
                                int T4, int OPL, int KC, int parts, cudaStream_t stream);
 bool route_fused_supported(int T4, int OPL);
-size_t route_fused_smem_bytes(int OPL, int KC, int x3, int nwst);
+size_t route_fused_smem_bytes(int OPL, int KC, int x3, int nwst, size_t wstage_bytes);
 
 }  // namespace srf
 
@@ -154,9 +154,10 @@ cudaError_t launch_uhat_gemm(const CUtensorMap& tmap, const UhatParams& p, int n
                              cudaStream_t stream);
 
 // ---- fused routing kernel: device-side descriptors ----
-struct alignas(64) FusedLayer {
-  CUtensorMap tmap;           // 5-D map over this layer's input capsules [B,S,H,d]
-  const float* Wf;            // [i][part][m][KC][128][4]
+constexpr int FZ_MAX_LAYERS = 16;
+struct FusedLayer {
+  const float* emb;           // this layer's input capsules [B,S,H,d]
+  const float* Wf;            // [i][m][part][KC][128][4]
   const float* ln_gamma;
   const float* ln_beta;
   const float* dropout_mask;
@@ -188,12 +189,28 @@ struct FusedParams {
   float* xV;                  // [slot][32][T][OP]       squashed outputs
   int* cnt_p;                 // [slot]
   int* cnt_v;                 // [slot][2]
+  int* oflag;                 // [slot][32] last epoch whose v row the output warp has taken
   int* progress;              // [layer][group][32] frames stored (SDR wavefront), or null
   int* abort_flag;
   int* host_abort;            // mapped host copy of the abort code
   int maxC, ngroups;
   int B, S, sdr, iters, NB;
-  int nwst;                   // W-tile ring stages
+  int nwst;                   // W ring stages
+  int gtiles;                 // W tiles (hi + lo images) per ring stage = one bulk copy
+  int wstage_bytes;           // ring stage stride
+  int xtile_bytes;            // x ring stage stride (widest layer)
+  unsigned long long* dbg;    // optional phase timers [CTA][16] (clock64 sums), null = off
+  // The geometry of every CTA's work, as kernel parameters: the MMA issuers derive their smem
+  // descriptors from it, and only values that are provably warp-uniform (parameters, blockIdx)
+  // stay on ptxas' uniform datapath.  CTA b serves layer l with cta_end[l-1] <= b % per_group <
+  // cta_end[l] (SDR; DR has one layer) as the c-th of C_l CTAs of its unit.
+  int per_group;
+  int n_layers;
+  int cta_end[FZ_MAX_LAYERS];
+  int layer_I[FZ_MAX_LAYERS];
+  int layer_opl[FZ_MAX_LAYERS];
+  int layer_KC[FZ_MAX_LAYERS];
+  int layer_KX[FZ_MAX_LAYERS];
 };
 cudaError_t launch_route_fused(const FusedParams& p, int T4, int OPL, int x3, int grid, size_t smem,
                                cudaStream_t stream);

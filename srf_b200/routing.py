@@ -87,9 +87,10 @@ _handles = {}
 
 def default_handle(device=None) -> Handle:
   dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-  key = dev.index or 0
+  # torch.device("cuda") carries no index: it means the CURRENT device, not device 0
+  key = dev.index if dev.index is not None else torch.cuda.current_device()
   if key not in _handles:
-    _handles[key] = Handle(dev)
+    _handles[key] = Handle(torch.device("cuda", key))
   return _handles[key]
 
 

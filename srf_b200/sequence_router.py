@@ -112,12 +112,16 @@ class RoutingStack:
     args = []
     for i in range(n):
       last = i == n - 1
+      # the packed-weight cache tag follows torch's in-place version counters, so an optimiser
+      # step (same storage, new values) can never be served from a stale packed copy
+      tag = hash((self._version, self.wgt[i]._version, self.bias[i]._version,
+                  self.wgt[i].data_ptr(), self.bias[i].data_ptr())) & 0x7FFFFFFFFFFFFFFF
       args.append(routing.LayerArgs(
           W=self.wgt[i], bias=self.bias[i], lpad=self.lpad, rpad=self.rpad, iters=self.iters,
           sdr=self.sdr, mask_class0=last, ln_gamma=self.ln_gamma[i], ln_beta=self.ln_beta[i],
           dropout_mask=None if dropout_masks is None else dropout_masks[i],
           head_gamma=self.lno_gamma if last else None, head_beta=self.lno_beta if last else None,
-          uhat_mode=self.uhat_mode, length_eps=self.length_eps, weights_version=self._version))
+          uhat_mode=self.uhat_mode, length_eps=self.length_eps, weights_version=tag or 1))
     return args
 
   def make_dropout_masks(self, B: int, S: int, generator=None):

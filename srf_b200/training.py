@@ -66,6 +66,8 @@ def warmup_lr(step: int, k: float, d_model: float, warmup_steps: float, max_lr: 
   """CustomSchedule.__call__ (train_helper.py:52-56): min(k * d_model^-0.5 * min(step^-0.5,
   step * warmup^-1.5), max_lr)."""
   step = float(step)
+  if step <= 0.0:
+    return 0.0   # tf: rsqrt(0) = inf, min(inf, 0 * warmup^-1.5) = 0
   return min(k * d_model ** -0.5 * min(step ** -0.5, step * warmup_steps ** -1.5), max_lr)
 
 
@@ -130,6 +132,8 @@ class TrainStep:
     flat = torch.cat([grads[k].reshape(-1) for k in self.names]).mul_(1.0 / self.global_batch)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
       dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-    self.opt.step(flat, warmup_lr(self.iteration, self.k, self.d_model, self.warmup_steps))
+    # Keras evaluates the schedule at optimizer.iterations BEFORE the increment (0 on the first
+    # apply_gradients: the first learning rate is 0); only Adam's bias correction uses iterations+1
+    self.opt.step(flat, warmup_lr(self.iteration - 1, self.k, self.d_model, self.warmup_steps))
     self.stack.mark_weights_changed()
     return loss

@@ -118,3 +118,41 @@ def test_average_checkpoints_is_the_mean_of_the_last_n(tmp_path):
   ck.load_state_dict(m, ck.read_checkpoint(out))
   want2 = np.mean([s["b0"].astype(np.float64) for s in states[2:]], axis=0)
   assert np.allclose(m.p["b0"].numpy(), want2, rtol=0, atol=1e-6)
+
+
+class FakeRouter:
+  """Stands in for SequenceRouter: front-end parameters appear only after load_frontend / the
+  first call, like the lazily built Keras layers of the reference."""
+
+  def __init__(self, seed):
+    self.stack = FakeStack(seed)
+    self.fe = {}
+
+  def load_frontend(self, params):
+    self.fe = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in params.items()}
+
+  def named_parameters(self):
+    return [("frontend/" + k, v) for k, v in sorted(self.fe.items())] + self.stack.named_parameters()
+
+
+def test_fresh_model_restores_its_frontend_and_strict_rejects_unknown_entries():
+  src = FakeRouter(3)
+  src.load_frontend({"dense_kernel": np.arange(6, dtype=np.float32).reshape(2, 3), "dense_bias": np.ones(3)})
+  state = ck.state_dict(src)
+  dst = FakeRouter(4)           # fresh: no front-end parameters yet
+  loaded = ck.load_state_dict(dst, state)
+  assert "frontend/dense_kernel" in loaded and "frontend/dense_bias" in loaded
+  for (n1, t1), (n2, t2) in zip(src.named_parameters(), dst.named_parameters()):
+    assert n1 == n2 and torch.equal(t1, t2)
+  state["frontend/not_a_parameter"] = np.zeros(3)
+  with pytest.raises(KeyError):
+    ck.load_state_dict(FakeRouter(5), {k: v for k, v in state.items() if k != "frontend/dense_bias"} |
+                       {"stray": np.zeros(2)})
+  # the reference's expect_partial(): extra entries are fine when not strict
+  ck.load_state_dict(FakeRouter(6), state | {"stray": np.zeros(2)}, strict=False)
+
+
+def test_warmup_schedule_starts_at_zero_like_keras():
+  from srf_b200 import training
+  assert training.warmup_lr(0, k=0.5, d_model=256, warmup_steps=4) == 0.0
+  assert training.warmup_lr(1, k=0.5, d_model=256, warmup_steps=4) == 0.5 * 256 ** -0.5 * 4 ** -1.5

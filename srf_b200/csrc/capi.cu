@@ -53,7 +53,7 @@ struct srf_handle {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled
   // fused routing kernel (routing_fused.cu)
   std::vector<PackedWeights> packed_fused;
-  int no_fused = 0;
+  int no_fused = 0, force_fused = 0;
   void* fz_tab = nullptr;        // device: FusedLayer[] + FusedItem[] + counters + progress
   size_t fz_tab_bytes = 0;
   float* fz_x = nullptr;         // device: exchange buffers (partial sums, squashed outputs)
@@ -154,6 +154,7 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_STREAM_STAGES")) h->max_stages = atoi(s);
   if (const char* s = getenv("SRF_BWD_ATOMICS")) h->bwd_atomics = atoi(s);
   if (const char* s = getenv("SRF_NO_FUSED")) h->no_fused = atoi(s);
+  if (const char* s = getenv("SRF_FORCE_FUSED")) h->force_fused = atoi(s);
   if (cudaHostAlloc((void**)&h->fz_host_abort, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
     *h->fz_host_abort = 0;
     if (cudaHostGetDevicePointer((void**)&h->fz_host_abort_dev, h->fz_host_abort, 0) != cudaSuccess)
@@ -778,6 +779,21 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
       rounds = 1;
       nslots = ngroups;
     }
+  }
+  // Policy (measured, profiles/r2_modes.md): a pass costs the fused kernel a fixed ~35k clk (the
+  // L2 exchange of the partial sums) plus ~3k clk per input capsule of the CTA's slice (tf32;
+  // 3 x TF32 issues three times the MMAs: ~9k).  With few capsules per CTA (TIMIT-sized SDR layers
+  // spread over 148 SMs) or in the 3 x TF32 mode on long slices the two-kernel path is faster.
+  {
+    int ncap_min = 1 << 30;
+    for (int l = 0; l < n; ++l) {
+      const int c = geo[l].I / Cl[sdr ? l : 0];
+      if (c < ncap_min) ncap_min = c;
+    }
+    const bool x3 = parts == 2;
+    bool take = x3 ? (sdr && ncap_min >= 8 && ncap_min <= 16) : !(sdr && ncap_min < 8);
+    if (h->force_fused > 0) take = true;
+    if (!take) return FUSED_FALLBACK;
   }
   std::vector<srf::FusedItem> items((size_t)rounds * grid);
   for (auto& itm : items) itm.layer = -1;

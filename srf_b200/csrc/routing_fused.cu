@@ -237,6 +237,24 @@ __device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
         : "memory");
 }
+// all MMAs of one capsule: NTA tiles x NKS K steps (x 3 in the 3 x TF32 build), no run-time
+// predicates between the instructions
+template <int NTA, int NKS, bool X3>
+__device__ __forceinline__ void mma_issue_capsule(uint32_t d_base, const uint32_t (&a_lo)[NTA], uint32_t b_lo,
+                                                  uint32_t blo_lo, uint32_t wtile16, uint32_t desc_hi,
+                                                  uint32_t idesc) {
+#pragma unroll
+  for (int m = 0; m < NTA; ++m) {
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      mma_tf32_lo(d_base + m * FZ_N, a_lo[m] + ks * 256, b_lo + ks * (2 * FZ_N), desc_hi, idesc, ks > 0);
+      if (X3) {
+        mma_tf32_lo(d_base + m * FZ_N, a_lo[m] + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), desc_hi, idesc, true);
+        mma_tf32_lo(d_base + m * FZ_N, a_lo[m] + ks * 256, blo_lo + ks * (2 * FZ_N), desc_hi, idesc, true);
+      }
+    }
+  }
+}
 __device__ __forceinline__ void mma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -658,18 +676,30 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               const uint32_t base1 = a_lo0 + ((gs + 1) % NWST) * wstage16 + (uint32_t)(tin - G) * wpair16;
               const uint32_t base2 = a_lo0 + ((gs + 2) % NWST) * wstage16 + (uint32_t)(tin - 2 * G) * wpair16;
 #ifndef SRF_FUSED_NOMMA
+              if (nt == NT && (nks == 2 || nks == 3 || nks == 5)) {
+                uint32_t al[NT];
 #pragma unroll
-              for (int m = 0; m < NT; ++m) {
-                if (m < nt) {
+                for (int m = 0; m < NT; ++m) {
                   const int t = tin + m;
-                  const uint32_t a_lo = (t < G ? base0 : (t < 2 * G ? base1 : base2)) + (uint32_t)m * wpair16;
+                  al[m] = (t < G ? base0 : (t < 2 * G ? base1 : base2)) + (uint32_t)m * wpair16;
+                }
+                if (nks == 3) mma_issue_capsule<NT, 3, X3>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else if (nks == 2) mma_issue_capsule<NT, 2, X3>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else mma_issue_capsule<NT, 5, X3>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+              } else {
 #pragma unroll
-                  for (int ks = 0; ks < 5; ++ks) {
-                    if (ks < nks) {
-                      mma_tf32_lo(d_base + m * FZ_N, a_lo + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, ks > 0);
-                      if (X3) {
-                        mma_tf32_lo(d_base + m * FZ_N, a_lo + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
-                        mma_tf32_lo(d_base + m * FZ_N, a_lo + ks * 256, blo_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                for (int m = 0; m < NT; ++m) {
+                  if (m < nt) {
+                    const int t = tin + m;
+                    const uint32_t a_lo = (t < G ? base0 : (t < 2 * G ? base1 : base2)) + (uint32_t)m * wpair16;
+#pragma unroll
+                    for (int ks = 0; ks < 5; ++ks) {
+                      if (ks < nks) {
+                        mma_tf32_lo(d_base + m * FZ_N, a_lo + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, ks > 0);
+                        if (X3) {
+                          mma_tf32_lo(d_base + m * FZ_N, a_lo + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                          mma_tf32_lo(d_base + m * FZ_N, a_lo + ks * 256, blo_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                        }
                       }
                     }
                   }

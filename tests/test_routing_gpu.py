@@ -303,7 +303,7 @@ def test_tensor_path_full_stack(case, mode):
   stack.load_oracle_params(p32)
   logits = stack.forward(emb.cuda())
   torch.cuda.synchronize()
-  assert "uhat_gemm_kernel" in stack.handle.last_kernel
+  assert "uhat_gemm_kernel" in stack.handle.last_kernel or "route_fused_kernel" in stack.handle.last_kernel
   assert rel_err(logits, ref_logits) < (TENSOR_TOL if iters == 1 else TENSOR_TOL_ITER)[mode]
   lens = [S] + [max(1, S - 3)] * (B - 1)
   assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(ref_logits, lens)
@@ -321,6 +321,7 @@ def test_streaming_kernel_is_deterministic_and_matches_register_variant(monkeypa
     B, S, H, d, O, D, lpad, rpad = case
     emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=3)
     outs = {}
+    monkeypatch.setenv("SRF_NO_FUSED", "1")   # this test is about the two-kernel path
     for ns in ("0", "1"):
       monkeypatch.setenv("SRF_NO_STREAM", ns)
       h = routing.Handle()
@@ -334,6 +335,107 @@ def test_streaming_kernel_is_deterministic_and_matches_register_variant(monkeypa
       outs[ns] = runs[0]
       h.close()
     assert rel_err(outs["0"], outs["1"].cpu()) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------
+# fused routing kernel (routing_fused.cu): u_hat from tcgen05 into TMEM, consumed in place; SDR
+# stacks as one layer-wavefront launch.  SRF_FORCE_FUSED=1 takes the policy out of the picture.
+# ----------------------------------------------------------------------------------------
+FUSED_LAYER_CASES = [
+    (2, 9, 6, 8, 5, 8, 1, 1),
+    (3, 5, 60, 8, 30, 8, 1, 1),
+    (2, 6, 30, 8, 63, 8, 1, 1),        # two blocks of 32 output capsules
+    (8, 5, 30, 8, 30, 8, 3, 3),
+    (64, 3, 60, 20, 30, 20, 2, 2),     # two frame groups
+    (5, 4, 30, 20, 32, 20, 2, 2),
+    (2, 5, 7, 16, 9, 16, 0, 0),        # single-frame window
+    (3, 4, 9, 4, 10, 12, 1, 0),        # d != D
+    (40, 6, 12, 8, 20, 8, 1, 1),       # a full and a ragged frame group
+    (70, 4, 6, 8, 7, 8, 0, 1),         # three frame groups
+]
+
+
+@pytest.fixture
+def fused_handle(monkeypatch):
+  from srf_b200 import routing
+  monkeypatch.setenv("SRF_FORCE_FUSED", "1")
+  h = routing.Handle()
+  yield h
+  h.close()
+
+
+@pytest.mark.parametrize("case", FUSED_LAYER_CASES)
+@pytest.mark.parametrize("mode", ["tf32", "fp32x3"])
+def test_fused_single_layer_matches_oracle(case, mode, fused_handle):
+  from srf_b200 import routing
+  B, S, H, d, O, D, lpad, rpad = case
+  emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=23)
+  for sdr in (True, False):
+    for iters, last in ((1, False), (3, True)):
+      ref = o.route_layer(emb.double(), W.double(), bias.double(), lpad, rpad, iters, sdr, last)
+      a = routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=lpad, rpad=rpad, iters=iters, sdr=sdr,
+                            mask_class0=last, uhat_mode=mode)
+      caps, _ = routing.route_layer_fwd(emb.cuda(), a, handle=fused_handle)
+      torch.cuda.synchronize()
+      assert "route_fused_kernel" in fused_handle.last_kernel
+      assert rel_err(caps, ref) < (TENSOR_TOL if iters == 1 else TENSOR_TOL_ITER)[mode], (sdr, iters, last)
+      if last:
+        assert torch.count_nonzero(caps[:, :, 0]) == 0
+
+
+@pytest.mark.parametrize("case", STACK_CASES, ids=[c[0] for c in STACK_CASES])
+@pytest.mark.parametrize("mode", ["tf32", "fp32x3"])
+def test_fused_stack_wavefront_matches_oracle_and_greedy_ctc(case, mode, fused_handle):
+  """SDR stacks run as ONE launch (layer wavefront through progress flags), DR stacks layer by layer;
+  LayerNorm parameters, head and every intermediate layer output are checked."""
+  from srf_b200 import RoutingStack
+  _, L, PH, CH, class_n, DIM, lpad, rpad, iters, sdr, B, S = case
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1)
+  p32 = o.init_params(shapes, class_n, seed=11, random_ln=True)
+  emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(12))
+  ref_logits, ref_caps = o.route_stack(emb.double(), p32.to(torch.float64), lpad, rpad, iters, sdr,
+                                       return_capsules=True)
+  stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, sdr, seed=0, uhat_mode=mode)
+  stack.handle = fused_handle
+  stack.load_oracle_params(p32)
+  logits, caps = stack.forward(emb.cuda(), return_capsules=True)
+  again = stack.forward(emb.cuda())
+  torch.cuda.synchronize()
+  assert "route_fused_kernel" in fused_handle.last_kernel
+  if sdr:
+    assert "SDR-wavefront layers=%d" % L in fused_handle.last_kernel
+  tol = (TENSOR_TOL if iters == 1 else TENSOR_TOL_ITER)[mode]
+  assert rel_err(logits, ref_logits) < tol
+  for i, (c, r) in enumerate(zip(caps[:-1], ref_caps[:-1])):
+    assert rel_err(c, r) < tol, "layer %d" % i
+  assert torch.equal(logits, again)          # fixed summation order: bit-identical relaunch
+  lens = [S] + [max(1, S - 3)] * (B - 1)
+  assert o.greedy_ctc(logits.cpu(), lens) == o.greedy_ctc(ref_logits, lens)
+
+
+def test_fused_training_mode_outputs(fused_handle):
+  """Dropout masks, LayerNorm, the saved pre-LayerNorm capsules and the einsum variant's length
+  epsilon (einsum:238) through the fused kernel's output warp."""
+  from srf_b200 import routing
+  B, S, H, d, O, D, lpad, rpad = 5, 7, 12, 8, 11, 8, 1, 2
+  emb, W, bias = _mk_layer(B, S, H, d, O, D, lpad + rpad + 1, seed=31)
+  g = torch.Generator().manual_seed(32)
+  gamma, beta = 1 + 0.1 * torch.randn(O * D, generator=g), 0.1 * torch.randn(O * D, generator=g)
+  hg, hb = 1 + 0.1 * torch.randn(O, generator=g), 0.1 * torch.randn(O, generator=g)
+  mask = (torch.rand(B, S, O, D, generator=g) < 0.9).float() / 0.9
+  for eps in (1e-7, 1e-9):
+    ref_raw = o.route_layer(emb.double(), W.double(), bias.double(), lpad, rpad, 1, True, True)
+    ref_caps = o.layer_norm(ref_raw.reshape(B, S, O * D), gamma.double(), beta.double()).reshape(B, S, O, D) * mask.double()
+    ref_logits = o.layer_norm(o.length(ref_caps, axis=-1, epsilon=eps), hg.double(), hb.double())
+    a = routing.LayerArgs(W=W.cuda(), bias=bias.cuda(), lpad=lpad, rpad=rpad, iters=1, sdr=True, mask_class0=True,
+                          ln_gamma=gamma.cuda(), ln_beta=beta.cuda(), dropout_mask=mask.cuda(), head_gamma=hg.cuda(),
+                          head_beta=hb.cuda(), uhat_mode="fp32x3", length_eps=eps)
+    caps, logits, raw = routing.route_layer_fwd_train(emb.cuda(), a, handle=fused_handle)
+    torch.cuda.synchronize()
+    assert "route_fused_kernel" in fused_handle.last_kernel
+    assert rel_err(raw, ref_raw) < 1e-4
+    assert rel_err(caps, ref_caps) < 1e-4
+    assert rel_err(logits, ref_logits) < 1e-4
 
 
 @pytest.mark.parametrize("name", ["sdr_i1_w3", "dr_i3_w7", "sdr_i2_w5"])

@@ -1,0 +1,21 @@
+import sys, os, json, torch
+sys.path.insert(0, '.')
+import bench
+from srf_b200 import RoutingStack
+def run(name, mode, B=None):
+    w = bench.WORKLOADS[name]
+    Bw, Sw = (B or w["B"]), (w["T"] + 3) // 4
+    st = RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"], w["lpad"], w["rpad"], w["iters"], w["sdr"], seed=0, uhat_mode=mode)
+    e = torch.randn(Bw, Sw, w["PH"], w["DIM"], device="cuda")
+    o = torch.empty(Bw, Sw, w["class_n"], device="cuda")
+    for _ in range(3): st.forward(e, out_logits=o)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): st.forward(e, out_logits=o)
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / 10, st.handle.last_kernel[:40]
+for name, B in (("cfg1", None), ("cfg2", None), ("cfg3", None), ("cfg3", 8), ("cfg3", 32)):
+    for mode in ("tf32", "fp32x3", "bf16"):
+        ms, k = run(name, mode, B)
+        print("%s B=%s %-7s fused=%s: %.3f ms  %s" % (name, B, mode, os.environ.get("SRF_NO_FUSED", "0") != "1", ms, k), flush=True)

@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- SRF routing-layer throughput on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg3|cfg2|cfg1] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg3|cfg2|cfg1] [--uhat tf32|fp32x3|bf16|fp32]
+    python bench.py --impl reference ...        # the CPU arm (oracle port; TensorFlow is not installable)
 
 A "step" is one forward pass of the routing stack (primary capsules -> CTC logits,
 tfsr/model/sequence_router_naive.py:145-193) over one synthetic batch.  Default workload is
 cfg-3 of BASELINE.json (SRF-SDR WSJ-shaped, 31 labels + blank, batch 64 x 1500 fbank frames
 = 64 x 375 routing frames, ITER=1), the configuration the metric "frames/sec at 1/2/4/8
-B200" is quoted on.  Multi-GPU: utterances are independent, every rank routes its own
-64-utterance shard with no data-path collective (weak scaling); value = all ranks' routing
-frames / max-over-ranks device time.
+B200" is quoted on; default arithmetic is the fused tcgen05 kernel (TF32 operands, u_hat never
+leaves the SM; 1e-2 tolerance class with identical greedy-CTC strings, see
+tests/test_routing_gpu.py::test_bench_mode_full_size_cfg3_parity).
 
-Prints ONE JSON line (rank 0).
+The JSON line (rank 0) carries
+  value / e2e   : every GPU routes its own 64-utterance batch, no collective (weak scaling);
+  strong        : the 64-utterance batch sharded over the N GPUs (64/N per GPU), as BASELINE.json words cfg-3;
+  train_cfg4    : the training step (fwd + CTC + bwd + NCCL gradient all-reduce + Adam), global batch 64 sharded;
+  roofline      : the dominant kernel against the bound of the fused design (tensor: derived TF32 peak);
+  cpu_baseline  : the oracle port on all host threads over the sample `--impl reference` times (N = 1).
 """
 from __future__ import annotations
 
@@ -120,12 +126,12 @@ def cpu_reference_run(w, n_utts, n_frames, repeats=1, seed=0):
   return n_utts * n_frames / best, best
 
 
-def cpu_sample_shape(w, big=False):
-  """Bounded sample of the workload for the CPU arm.  Per-frame cost is independent of S and
-  nearly independent of B.  big=True: the ~10 s sample used once for `cpu_baseline`; else the
-  per-step sample of `--impl reference` (steps+warmup of them must finish within minutes)."""
+def cpu_sample_shape(w):
+  """Bounded sample of the workload for BOTH CPU legs (`cpu_baseline` of the GPU arm and every step
+  of `--impl reference`), so that the two report the same thing.  Per-frame cost of the CPU path is
+  independent of S and nearly independent of B; the sample is about 4 s of work on 16 cores."""
   if w["DIM"] >= 16:
-    return (16, 375) if big else (4, 64)
+    return (16, 375)
   return (w["B"], 75)
 
 
@@ -157,6 +163,23 @@ def run_reference_arm(args, w, rank, world):
   print(json.dumps(line), flush=True)
 
 
+def build_stack(w, dev, uhat, inn_dropout=0.1):
+  from srf_b200 import RoutingStack
+  return RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"], w["lpad"],
+                      w["rpad"], w["iters"], w["sdr"], device=dev, seed=0, uhat_mode=uhat,
+                      inn_dropout=inn_dropout)
+
+
+UHAT_DESC = {
+    "fp32": "FP32 CUDA cores, fused FP32 kernel",
+    "tf32": "fused routing kernel: tcgen05 TF32 MMA into TMEM, u_hat consumed in place (never in HBM), "
+            "SDR stack as one layer-wavefront launch (1e-2 tolerance class, identical greedy CTC)",
+    "bf16": "two kernels: tcgen05 TF32 MMA, bf16 u_hat materialised in HBM, streaming routing kernel",
+    "fp32x3": "3 x TF32 split (fp32-class u_hat, 1e-4 tolerance class); fused kernel or two-kernel path "
+              "by the library's policy",
+}
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -165,10 +188,10 @@ def main():
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other configs")
-  ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "bf16", "fp32x3"],
-                  help="u_hat arithmetic: bf16 = tcgen05 TF32 MMA + bf16 u_hat storage (default), "
-                       "tf32 = same with fp32 storage, fp32 = exact FP32 CUDA-core kernel")
+  ap.add_argument("--no-also", action="store_true", help="skip the strong-scaling, training and other-config legs")
+  ap.add_argument("--uhat", default="tf32", choices=["fp32", "tf32", "bf16", "fp32x3"],
+                  help="u_hat arithmetic: tf32 = fused tcgen05 kernel (default), fp32x3 = the 1e-4 class, "
+                       "bf16 = round-1 two-kernel path with bf16 u_hat in HBM, fp32 = CUDA-core kernel")
   args = ap.parse_args()
   w = dict(WORKLOADS[args.workload])
 
@@ -191,11 +214,8 @@ def main():
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
-  from srf_b200 import RoutingStack
   B, S = w["B"], (w["T"] + 3) // 4
-  stack = RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"],
-                       w["lpad"], w["rpad"], w["iters"], w["sdr"], device=dev, seed=0,
-                       uhat_mode=args.uhat)
+  stack = build_stack(w, dev, args.uhat)
   g = torch.Generator().manual_seed(1000 + rank)
   n_bufs = 2
   host_emb = [torch.randn(B, S, w["PH"], w["DIM"], generator=g).pin_memory() for _ in range(n_bufs)]
@@ -209,6 +229,7 @@ def main():
     torch.cuda.synchronize()
 
   def timed(fn, steps):
+    """`steps` calls between barriers, CUDA events on the launch stream, max over ranks (ms)."""
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
@@ -245,6 +266,7 @@ def main():
   sampler.start()
   ms_total = timed(step_resident, args.steps)
   launches = stack.handle.launches - l0
+
   def e2e_region(steps):
     for i in range(steps):
       step_e2e(i)
@@ -252,17 +274,7 @@ def main():
       checks.append(float(pipe.result()[0, 0, 1]))
 
   e2e_region(2)
-  start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  barrier()
-  start.record()
-  e2e_region(args.steps)          # returns once the last logits are on the host
-  end.record()
-  barrier()
-  ms_e2e = start.elapsed_time(end)
-  if world > 1:
-    tt = torch.tensor([ms_e2e], device=dev)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_e2e = tt.item()
+  ms_e2e = timed(lambda i: e2e_region(args.steps) if i == 0 else None, 1)   # returns once the last logits are on the host
   # same steps once more with every kernel bracketed by CUDA events on its launch stream
   stack.handle.profile_begin()
   timed(step_resident, args.steps)
@@ -281,7 +293,8 @@ def main():
       peaks = json.load(f)
   except Exception:  # pylint: disable=broad-except
     pass
-  p_tensor = peaks.get("bf16_tflops_sustained", 1400.0)
+  p_bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+  p_tf32 = p_bf16 / 2.0          # TF32 is not in MEASURED_PEAKS.json: half the measured bf16 rate, "derived"
   p_hbm = peaks.get("hbm_gbs", 6650.0)
   peak_src = "measured" if peaks else "fallback"
   f_uhat, f_route, bytes_frame, weights = algorithmic_work(w)
@@ -289,47 +302,50 @@ def main():
   frames_rank = B * S
   sm_mhz = clocks.get("sm_mhz") or 1965
   fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-  # what the fused design is judged on: t_roof = max(tensor time, HBM time)
-  t_roof = max(f_uhat * frames_rank / (p_tensor * 1e12),
-               (bytes_frame * frames_rank + weights) / (p_hbm * 1e9))
+  # the fused roofline: t_roof = max(tensor time of the u_hat contraction, HBM time
+  # of the algorithmic bytes); the dense contraction binds for every config of BASELINE.json
+  t_tensor = f_uhat * frames_rank / (p_tf32 * 1e12)
+  t_hbm = (bytes_frame * frames_rank + weights) / (p_hbm * 1e9)
+  t_roof = max(t_tensor, t_hbm)
   kernel_ms = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                for k, v in kprof.items()}
   dom = max(("uhat_gemm", "routing"), key=lambda k: kprof[k][0])
-  dom_ms_launch = kprof[dom][0] / max(1, kprof[dom][1])
-  esize = {"fp32": 0, "tf32": 4, "bf16": 2, "fp32x3": 4}[args.uhat]
-  uhat_elems = sum(I * O * D for (I, O, D, d) in shapes_of(w))          # per routing frame, all layers
+  dom_launches = max(1, kprof[dom][1])
+  dom_ms_launch = kprof[dom][0] / dom_launches
+  fused = "route_fused_kernel" in kernel_name
   traffic = None
   try:
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-      traffic = json.load(f).get("%s/%s/%s" % (args.workload, args.uhat, dom))
+      traffic = json.load(f).get("%s/%s/%s" % (args.workload, args.uhat, "route_fused" if fused else dom))
   except Exception:  # pylint: disable=broad-except
     pass
-  if args.uhat == "fp32":
-    achieved = f_uhat * frames_rank / n_layers / (dom_ms_launch / 1e3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": p_tensor, "unit": "TFLOP/s",
-                "frac": achieved / p_tensor, "traffic": traffic,
-                "note": "fused FP32 kernel: u_hat FLOPs (2 I O D d per frame-layer) per launch / launch time; "
-                        "u_hat runs on the FP32 pipe in this mode"}
-  else:
-    # two-kernel tensor path: both kernels are HBM-bound on the materialised u_hat
-    # (SURVEY.md 8d): algorithmic bytes per launch = frames * I*O*D * sizeof(store) of that
-    # layer (+ the capsules read/written), averaged over the layers of a step
-    io_bytes = bytes_frame * frames_rank / n_layers
-    alg_bytes = uhat_elems * esize * frames_rank / n_layers + io_bytes
-    achieved = alg_bytes / (dom_ms_launch / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": p_hbm, "unit": "GB/s",
-                "frac": achieved / p_hbm, "traffic": traffic,
-                "note": "dominant kernel %s; algorithmic bytes/launch = frames*I*O*D*%d B of materialised "
-                        "u_hat (%s) + capsule I/O, avg over the %d layer launches of a step"
-                        % (dom, esize, "written" if dom == "uhat_gemm" else "read", n_layers)}
-  roofline.update({
-      "peak_source": peak_src, "kernel": kernel_name, "dominant": dom, "launch_ms": dom_ms_launch,
-      "kernel_ms": kernel_ms,
+  # the dominant kernel against the bound of the fused design: algorithmic u_hat FLOPs of the
+  # launches' share of the step / measured launch time, peak = derived TF32
+  share = dom_launches / args.steps                      # launches of the dominant kernel per step
+  achieved = f_uhat * frames_rank / share / (dom_ms_launch / 1e3) / 1e12
+  uhat_elems = sum(I * O * D for (I, O, D, d) in shapes_of(w))          # per routing frame, all layers
+  roofline = {
+      "bound": "tensor" if t_tensor >= t_hbm else "hbm", "achieved": achieved, "peak": p_tf32, "unit": "TFLOP/s",
+      "frac": achieved / p_tf32, "traffic": traffic,
+      "note": "dominant kernel %s (%d launch(es) per step); achieved = algorithmic u_hat FLOPs (2 I O D d per "
+              "frame-layer, SURVEY.md 8d) per launch / CUDA-event launch time; peak = TF32 derived as half the "
+              "measured sustained bf16 GEMM rate" % ("route_fused_kernel" if fused else dom, round(share)),
+      "peak_source": peak_src + " (bf16 sustained / 2: derived TF32)", "kernel": kernel_name, "dominant": dom,
+      "launch_ms": dom_ms_launch, "kernel_ms": kernel_ms,
       "fused_roofline_frac": t_roof / (ms_step / 1e3),
-      "tensor_frac_uhat": f_uhat * frames_rank / (ms_step / 1e3) / 1e12 / p_tensor,
       "hbm_frac_fused_min": (bytes_frame * frames_rank + weights) / (ms_step / 1e3) / 1e9 / p_hbm,
       "fp32_route_frac": f_route * frames_rank / (ms_step / 1e3) / 1e12 / fp32_peak,
-  })
+  }
+  if fused:
+    # what actually bounds the fused kernel: every time step re-streams the layer's weights from L2
+    # into shared memory (measured bulk-copy ingest 60-70 B/clk/SM = 17-19 TB/s, profiles/r2_ubench.txt)
+    groups = (B + 31) // 32
+    w_bytes_step = groups * S * weights * (2 if args.uhat == "fp32x3" else 1) * (32.0 / 30.0)
+    roofline["l2_weight_stream"] = {"bytes_per_step": w_bytes_step, "achieved_gbs": w_bytes_step / (ms_step / 1e3) / 1e9,
+                                    "measured_l2_to_smem_gbs": 17400.0}
+  else:
+    esize = {"fp32": 0, "tf32": 4, "bf16": 2, "fp32x3": 4}[args.uhat]
+    roofline["materialised_uhat_gbs"] = (uhat_elems * esize * frames_rank / n_layers + bytes_frame * frames_rank / n_layers) / (dom_ms_launch / 1e3) / 1e9
 
   line = {
       "metric": "routing_frames_per_sec", "value": value, "unit": "routing frames/s",
@@ -337,15 +353,13 @@ def main():
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "fp32x3": "f32"}[args.uhat], "data": "synthetic",
       "config": {"workload": w["desc"], "global_batch": B * world, "routing_frames_per_utt": S,
-                 "fbank_frames_per_sec": value * 4,
-                 "uhat": {"fp32": "FP32 CUDA cores, fused", "tf32": "tcgen05 TF32 MMA, fp32 u_hat in HBM",
-                          "bf16": "tcgen05 TF32 MMA, bf16 u_hat in HBM (1e-2 tolerance mode)",
-                          "fp32x3": "tcgen05 3 x TF32 split MMA (fp32-class), fp32 u_hat in HBM "
-                                    "(1e-4 tolerance mode)"}[args.uhat],
-                 "parallelism": "dp%d (utterance shards, no collective)" % world,
-                 "l2": "working set per step (inputs %d MB x2 rotating + weights %d MB + u_hat %d MB/layer) > 126 MB L2"
-                       % (host_emb[0].numel() * 4 >> 20, weights >> 20,
-                          (uhat_elems * esize * frames_rank // n_layers) >> 20)},
+                 "fbank_frames_per_sec": value * 4, "uhat": UHAT_DESC[args.uhat],
+                 "parallelism": "dp%d: every GPU routes its own 64 utterances, no collective (weak); the sharded "
+                                "64-utterance batch is under `strong`, the training step with the gradient "
+                                "all-reduce under `train_cfg4`" % world,
+                 "l2": "working set per step (inputs %d MB x2 rotating + packed weights %d MB + inter-layer capsules "
+                       "%d MB) > 126 MB L2" % (host_emb[0].numel() * 4 >> 20, weights >> 20,
+                                               (B * S * 600 * 4 * (n_layers - 1)) >> 20)},
       "e2e": {"value": e2e_value, "unit": "routing frames/s",
               "h2d_bytes_per_step": host_emb[0].numel() * 4 * world,
               "d2h_bytes_per_step": host_logits.numel() * 4 * world},
@@ -353,38 +367,27 @@ def main():
       "clocks": clocks,
       "roofline": roofline,
   }
-  if world == 1 and not args.no_also:
-    # the other single-GPU configurations of BASELINE.json, same build, short runs (not the
-    # headline: parity-test cases that are cheap enough to time beside it)
-    line["also"] = {}
-    for name in sorted(WORKLOADS):
-      if name == args.workload:
-        continue
-      ww = WORKLOADS[name]
-      Bw, Sw = ww["B"], (ww["T"] + 3) // 4
-      st2 = RoutingStack(ww["L"], ww["PH"], ww["CH"], ww["class_n"], ww["DIM"], ww["DIM"], ww["DIM"],
-                         ww["lpad"], ww["rpad"], ww["iters"], ww["sdr"], device=dev, seed=0,
-                         uhat_mode=args.uhat)
-      e2 = torch.randn(Bw, Sw, ww["PH"], ww["DIM"], device=dev)
-      o2 = torch.empty(Bw, Sw, ww["class_n"], device=dev)
-      for _ in range(3):
-        st2.forward(e2, out_logits=o2)
-      ms2 = timed(lambda i: st2.forward(e2, out_logits=o2), 20) / 20
-      line["also"][name] = {"workload": ww["desc"], "ms_per_step": ms2,
-                            "value": Bw * Sw / (ms2 / 1e3), "unit": "routing frames/s",
-                            "note": "inputs resident; working set fits L2"}
-  if world == 1 and not args.no_also:
-    # cfg-4 (BASELINE.json configs[3]) at its per-GPU share on 8 GPUs: fwd + CTC + bwd + Adam of the
-    # WSJ-shaped stack on 8 x 375 routing frames, everything in the library (tools/train_bench.py
-    # runs the full global batch under torchrun with the NCCL gradient all-reduce)
+
+  if not args.no_also:
+    # ---- cfg-3 as BASELINE.json words it: the 64-utterance batch SHARDED over the N GPUs ----
+    Bs = max(1, B // world)
+    st_s = stack if world == 1 else build_stack(w, dev, args.uhat)
+    e_s = dev_emb[0][:Bs].contiguous()
+    o_s = torch.empty(Bs, S, w["class_n"], device=dev)
+    for _ in range(3):
+      st_s.forward(e_s, out_logits=o_s)
+    ms_s = timed(lambda i: st_s.forward(e_s, out_logits=o_s), 10) / 10
+    line["strong"] = {"scaling": "strong", "workload": w["desc"] + ", sharded: %d utterances per GPU" % Bs,
+                      "global_batch": Bs * world, "ms_per_step": ms_s, "value": Bs * world * S / (ms_s / 1e3),
+                      "unit": "routing frames/s", "kernel": st_s.handle.last_kernel.split(" ")[0]}
+    # ---- cfg-4: training step of the WSJ-shaped stack, global batch 64 sharded, NCCL all-reduce ----
     from srf_b200 import training
     w4 = WORKLOADS["cfg3"]
-    B4, S4 = 8, (w4["T"] + 3) // 4
-    st4 = RoutingStack(w4["L"], w4["PH"], w4["CH"], w4["class_n"], w4["DIM"], w4["DIM"], w4["DIM"],
-                       w4["lpad"], w4["rpad"], w4["iters"], w4["sdr"], device=dev, seed=0,
-                       inn_dropout=0.1, uhat_mode=args.uhat)
-    tr4 = training.TrainStep(st4, 64)
-    g4 = torch.Generator().manual_seed(4)
+    B4, S4 = max(1, 64 // world), (w4["T"] + 3) // 4
+    train_mode = "bf16" if args.uhat in ("tf32", "bf16") else args.uhat
+    st4 = build_stack(w4, dev, train_mode)
+    tr4 = training.TrainStep(st4, B4 * world)
+    g4 = torch.Generator().manual_seed(4 + rank)
     e4 = torch.randn(B4, S4, w4["PH"], w4["DIM"], generator=g4).to(dev)
     lab4 = torch.randint(1, w4["class_n"] - 1, (B4, S4 // 3), generator=g4).to(dev)
     il4 = torch.full((B4,), S4, device=dev)
@@ -392,18 +395,39 @@ def main():
     for _ in range(2):
       tr4.step(e4, lab4, il4, ll4)
     ms4 = timed(lambda i: tr4.step(e4, lab4, il4, ll4), 3) / 3
-    line["also"]["cfg4_train_step_share"] = {
-        "workload": "SRF-SDR WSJ-shaped training step (fwd + CTC loss + bwd + Adam), 8 x 375 routing "
-                    "frames = one GPU's share of the 64-utterance batch on 8 GPUs",
-        "ms_per_step": ms4, "value": B4 * S4 / (ms4 / 1e3), "unit": "routing frames/s"}
+    line["train_cfg4"] = {
+        "scaling": "strong",
+        "workload": "SRF-SDR WSJ-shaped training step (fwd + CTC loss + bwd + NCCL all-reduce of %d gradient "
+                    "floats + Adam), global batch %d x 375 routing frames, %d utterances per GPU"
+                    % (tr4.opt.flat.numel(), B4 * world, B4),
+        "uhat": train_mode, "ms_per_step": ms4, "value": B4 * world * S4 / (ms4 / 1e3), "unit": "routing frames/s"}
     del st4, tr4
+  if world == 1 and not args.no_also:
+    # the other single-GPU configurations of BASELINE.json and the other tolerance class on the
+    # headline config, same build, short runs (not the headline)
+    line["also"] = {}
+    for name, mode in [(n, args.uhat) for n in sorted(WORKLOADS) if n != args.workload] + \
+                      [(args.workload, "fp32x3" if args.uhat != "fp32x3" else "tf32")]:
+      ww = WORKLOADS[name]
+      Bw, Sw = ww["B"], (ww["T"] + 3) // 4
+      st2 = build_stack(ww, dev, mode)
+      e2 = torch.randn(Bw, Sw, ww["PH"], ww["DIM"], device=dev)
+      o2 = torch.empty(Bw, Sw, ww["class_n"], device=dev)
+      for _ in range(3):
+        st2.forward(e2, out_logits=o2)
+      ms2 = timed(lambda i: st2.forward(e2, out_logits=o2), 10) / 10
+      line["also"]["%s_%s" % (name, mode)] = {
+          "workload": ww["desc"], "uhat": mode, "ms_per_step": ms2, "value": Bw * Sw / (ms2 / 1e3),
+          "unit": "routing frames/s", "kernel": st2.handle.last_kernel.split(" ")[0],
+          "note": "inputs resident" + ("; 1e-4 tolerance class" if mode == "fp32x3" else "")}
+      del st2
   if rank == 0 and not args.no_cpu_baseline and world == 1:
-    n_utts, n_frames = cpu_sample_shape(w, big=True)
+    n_utts, n_frames = cpu_sample_shape(w)
     fps, dt = cpu_reference_run(w, n_utts, n_frames, repeats=2)
     line["cpu_baseline"] = {"value": fps, "unit": "routing frames/s", "cores": os.cpu_count(),
                             "kind": "port",
-                            "sample": "%d utterances x %d routing frames of the same model, best of 2 x %.1f s"
-                                      % (n_utts, n_frames, dt)}
+                            "sample": "%d utterances x %d routing frames of the same model, best of 2 x %.1f s "
+                                      "(the sample `--impl reference` times per step)" % (n_utts, n_frames, dt)}
   if rank == 0:
     print(json.dumps(line), flush=True)
   if world > 1:

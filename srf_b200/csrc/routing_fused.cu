@@ -211,10 +211,19 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+// bulk copy global -> shared with an L2 eviction policy: the packed weights are re-read every time
+// step by every frame group and must stay resident in L2 while capsules and exchange buffers
+// stream through it (without the hint ncu showed 38 GB of DRAM reads per cfg-3 step)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                           uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], TF32; descriptors given as (low word, shared high word)
@@ -754,6 +763,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
     // every capsule that has a tile in the stage (so the issuers can never starve on x).
     uint32_t n_x = 0, n_w = 0;
     const uint32_t sW_a = ptx::smem_u32(sW);
+    const uint64_t w_policy = l2_policy_evict_last();
     for (int it = 0; it < p.rounds; ++it) {
       const FusedItem item = p.items[(size_t)it * gridDim.x + blockIdx.x];
       if (item.layer < 0) continue;
@@ -838,7 +848,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
             mbar_arrive_a(w_full + 8u * ws);
 #else
             mbar_expect_tx_a(w_full + 8u * ws, bytes);
-            bulk_g2s_a(sW_a + (uint32_t)ws * wstage, wsrc + (size_t)t0 * wpair, bytes, w_full + 8u * ws);
+            bulk_g2s_a(sW_a + (uint32_t)ws * wstage, wsrc + (size_t)t0 * wpair, bytes, w_full + 8u * ws, w_policy);
 #endif
           }
           ++n_w;

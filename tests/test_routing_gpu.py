@@ -519,6 +519,63 @@ def test_full_size_cfg3_properties():
   assert o.greedy_ctc(e_sl[:, :safe].cpu(), lens) == o.greedy_ctc(ref[:, :safe], lens)
 
 
+@pytest.mark.parametrize("mode", ["exact", "tf32"])
+def test_inference_after_an_in_place_weight_update_uses_the_new_weights(mode):
+  """The packed-weight cache is keyed on torch's in-place version counters: an optimiser step that
+  rewrites W / bias in place (same storage) must not be served from the stale packed copy."""
+  from srf_b200 import RoutingStack
+  L, PH, CH, class_n, DIM, lpad, rpad = 3, 12, 10, 9, 8, 1, 1
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1)
+  p32 = o.init_params(shapes, class_n, seed=4, random_ln=True)
+  emb = torch.randn(3, 6, PH, DIM, generator=torch.Generator().manual_seed(6))
+  stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, 1, True, seed=0, uhat_mode=mode)
+  stack.load_oracle_params(p32)
+  before = stack.forward(emb.cuda()).clone()
+  with torch.no_grad():
+    for w, b in zip(stack.wgt, stack.bias):      # what torch.optim does: in-place, same pointers
+      w.mul_(1.25)
+      b.add_(0.05)
+  after = stack.forward(emb.cuda())
+  torch.cuda.synchronize()
+  p_new = o.StackParams([w.cpu() for w in stack.wgt], [b.cpu() for b in stack.bias], p32.ln_gamma, p32.ln_beta,
+                        p32.lno_gamma, p32.lno_beta)
+  ref = o.route_stack(emb.double(), p_new.to(torch.float64), lpad, rpad, 1, True)
+  assert rel_err(after, ref) < (1e-4 if mode == "exact" else 5e-3)
+  assert rel_err(before, ref) > 1e-2            # the update really changed the function
+
+
+def test_bench_mode_full_size_cfg3_parity():
+  """The mode bench.py's headline is measured in (uhat_mode tf32 = fused kernel, TF32 operands,
+  u_hat never rounded for storage) on the full BASELINE.json cfg-3 batch: north_star's bar for the
+  reduced-precision class is 1e-2 relative and IDENTICAL greedy-CTC strings -- against the exact
+  kernel on a slice of the batch and against the float64 oracle on the causal prefix."""
+  from srf_b200 import RoutingStack
+  L, PH, CH, class_n, DIM, lpad, rpad = 10, 60, 30, 32, 20, 2, 2
+  B, S = 64, 375
+  emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(5)).cuda()
+  exact = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, 1, True, seed=9, uhat_mode="fp32")
+  fast = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, 1, True, seed=9, uhat_mode="tf32")
+  a = fast.forward(emb)
+  a2 = fast.forward(emb)
+  torch.cuda.synchronize()
+  assert "route_fused_kernel" in fast.handle.last_kernel and "SDR-wavefront layers=10" in fast.handle.last_kernel
+  assert torch.equal(a, a2) and torch.isfinite(a).all()
+  assert (a.argmax(-1) != 0).all()
+  sl = [3, 40, 63]
+  e_sl = exact.forward(emb[sl].contiguous())
+  torch.cuda.synchronize()
+  assert rel_err(a[sl], e_sl.cpu()) < 1e-2
+  lens = [S, S - 7, S - 100]
+  assert o.greedy_ctc(a[sl].cpu(), lens) == o.greedy_ctc(e_sl.cpu(), lens)
+  p = o.StackParams([w.cpu() for w in exact.wgt], [b.cpu() for b in exact.bias],
+                    [g.cpu() for g in exact.ln_gamma], [b.cpu() for b in exact.ln_beta],
+                    exact.lno_gamma.cpu(), exact.lno_beta.cpu())
+  ref = o.route_stack(emb[sl[:2], :48].cpu().double(), p.to(torch.float64), lpad, rpad, 1, True)
+  safe = 48 - L * rpad     # SDR is causal except for the right context of the 10 layers
+  assert rel_err(a[sl[:2], :safe], ref[:, :safe]) < 1e-2
+  assert o.greedy_ctc(a[sl[:2], :safe].cpu(), [safe, safe]) == o.greedy_ctc(ref[:, :safe], [safe, safe])
+
+
 # ----------------------------------------------------------------------------------------
 # backward (cfg-4): gradients against torch autograd of the oracle (float64)
 # ----------------------------------------------------------------------------------------

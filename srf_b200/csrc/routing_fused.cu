@@ -102,6 +102,7 @@ constexpr int FZ_N = 32;                 // frames per group = MMA N
 constexpr int FZ_TF = 16;                // frames per team
 constexpr int FZ_MATH_WARPS = 8;
 constexpr int FZ_THREADS = 384;          // 4 service warps + 8 math warps
+constexpr int FZ_CAP_RING = 8;           // capsule-completion barriers (>= x ring depth and TMEM buffers)
 constexpr int FZ_XST_MAX = 8;            // x-tile ring depth (tf32; the 3 x TF32 build keeps two images: 4)
 constexpr long long FZ_TIMEOUT = 6000000000ll;  // ~3 s of SM clocks
 
@@ -562,10 +563,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
   const uint32_t w_full = ptx::smem_u32(bars);               // [NWST]   (8 bytes each)
   const uint32_t w_empty = w_full + 8u * (uint32_t)NWST;     // [NWST]
   const uint32_t x_full = w_empty + 8u * (uint32_t)NWST;     // [XST]
-  const uint32_t x_empty = x_full + 8u * XST;             // [XST]
-  const uint32_t t_full = x_empty + 8u * XST;             // [NBUF]
-  const uint32_t t_empty = t_full + 8u * NBUF;               // [NBUF]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NWST + 2 * XST + 2 * NBUF);
+  // cap_done[n % 8]: the MMAs of capsule n have retired -- ONE tcgen05.commit per capsule tells the
+  // routing warps that its TMEM buffer is full and the x loader that its x slot is free (a commit
+  // costs the issuing thread ~350 clk)
+  const uint32_t cap_done = x_full + 8u * XST;            // [FZ_CAP_RING]
+  const uint32_t t_empty = cap_done + 8u * FZ_CAP_RING;   // [NBUF]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NWST + XST + FZ_CAP_RING + NBUF);
   volatile int* s_dead = reinterpret_cast<volatile int*>(tmem_ptr + 1);
 
   Waiter wt{p.abort_flag, p.host_abort, s_dead};
@@ -576,12 +579,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
       ptx::mbar_init(bars + s, 1);
       ptx::mbar_init(bars + NWST + s, 2);   // w_empty: one commit per MMA issuer
     }
-    for (int s = 0; s < XST; ++s) {
-      ptx::mbar_init(bars + 2 * NWST + s, 32);   // x_full: every lane of the loader warp
-      ptx::mbar_init(bars + 2 * NWST + XST + s, 1);
-    }
-    for (int s = 0; s < NBUF; ++s) ptx::mbar_init(bars + 2 * NWST + 2 * XST + s, 1);
-    for (int s = 0; s < NBUF; ++s) ptx::mbar_init(bars + 2 * NWST + 2 * XST + NBUF + s, FZ_MATH_WARPS);
+    for (int s = 0; s < XST; ++s) ptx::mbar_init(bars + 2 * NWST + s, 32);   // x_full: every lane of the loader warp
+    for (int s = 0; s < FZ_CAP_RING; ++s) ptx::mbar_init(bars + 2 * NWST + XST + s, 1);
+    for (int s = 0; s < NBUF; ++s) ptx::mbar_init(bars + 2 * NWST + XST + FZ_CAP_RING + s, FZ_MATH_WARPS);
     ptx::fence_barrier_init();
   }
   // constant part of the x tiles: chunk KX carries the 1 that multiplies the bias column of W
@@ -738,8 +738,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               if (pass_end) tin = 0;
             }
             if (mine) {
-              mma_commit_a(t_full + 8u * (uint32_t)(n_t % NBUF));
-              mma_commit_a(x_empty + 8u * (uint32_t)(n_x % XST));
+              mma_commit_a(cap_done + 8u * (uint32_t)(n_t % FZ_CAP_RING));
               FZ_MK(4)
 #ifdef SRF_FUSED_TIMERS
               ++ncap_tr;
@@ -799,7 +798,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
             const bool ok = frame_ok && s >= 0 && s < p.S;
             const float* src = base + ((size_t)(ok ? s : 0) * H + h) * d;
             const int xs = n_x % XST;
-            wt.mbar(x_empty + 8u * xs, ((n_x / XST) & 1) ^ 1, 102);
+            // the slot's previous tenant was capsule n_x - XST
+            if (n_x >= (uint32_t)XST) {
+              const uint32_t prev = n_x - (uint32_t)XST;
+              wt.mbar(cap_done + 8u * (prev % FZ_CAP_RING), (prev / FZ_CAP_RING) & 1, 102);
+            }
             const uint32_t dst = ptx::smem_u32(sX) + (uint32_t)xs * xtile + (uint32_t)lane * 16u;
             if (!X3) {
               const uint32_t nbytes = ok ? 16u : 0u;
@@ -1112,7 +1115,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
             const uint32_t capA = n_t + (uint32_t)n, capB = capA - 1u;
             const int bufA = capA % NBUF, bufB = capB % NBUF;
             if (doA) {
-              wt.mbar(t_full + 8u * bufA, (capA / NBUF) & 1, 110);
+              wt.mbar(cap_done + 8u * (capA % FZ_CAP_RING), (capA / FZ_CAP_RING) & 1, 110);
               ptx::tc_fence_after();
             }
             FZ_TK(1)

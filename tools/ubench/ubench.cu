@@ -534,15 +534,23 @@ __global__ void __launch_bounds__(384, 1) mma3_kernel(int variant, int ncaps, un
     const uint32_t b_lo0 = (((smem_u32(sm) + 65536) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
     long long t0 = clock64();
     for (int cap = 0; cap < ncaps; ++cap) {
-      const uint32_t a_base = a_lo0 + (uint32_t)(cap % 3) * 256u;   // varies per capsule
+      uint32_t a_base = a_lo0 + (uint32_t)(cap % 3) * 256u;   // varies per capsule
+      if (variant & 8) a_base = a_lo0 + (uint32_t)(cap & 1) * 3840u * 0u;   // same base; tiles below are 12 KB apart (streaming 60 KB)
       const uint32_t b_base = b_lo0 + (uint32_t)(cap & 7) * 192u;
       const uint32_t d_base = tm + (uint32_t)(cap % 3) * 160u;
-      if ((variant & 1) == 0) {
+      if (variant & 8) {
+        // real tile geometry: tile m at +12 KB (768 x 16 B), K step at +4 KB: 60 KB of A per capsule
 #pragma unroll
         for (int m = 0; m < 5; ++m)
 #pragma unroll
           for (int ks = 0; ks < 3; ++ks)
             mma_lo(d_base + m * 32, a_base + m * 768 + ks * 256, b_base + ks * 64, hi, idesc, ks > 0);
+      } else if ((variant & 1) == 0) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)
+            mma_lo(d_base + m * 32, a_base + (m & 0) * 768 + (ks & 0) * 256, b_base + ks * 64, hi, idesc, ks > 0);
       } else {
         // runtime split of the capsule's tiles over two ring stages (select per tile)
         const int split = 1 + (cap & 3);
@@ -585,10 +593,10 @@ void run_mma3() {
   unsigned long long* clk; CK(cudaMalloc(&clk, 16 * 1024));
   CK(cudaFuncSetAttribute(mma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   const int ncaps = 100;
-  for (int variant : {0, 2, 4, 6}) {
+  for (int variant : {0, 8, 10}) {
     for (int rep = 0; rep < 2; ++rep) { mma3_kernel<<<148, 384, 98304>>>(variant, ncaps, clk); CK(cudaDeviceSynchronize()); }
     unsigned long long h[2]; CK(cudaMemcpy(h, clk, 16, cudaMemcpyDeviceToHost));
-    printf("mma3 variant %d (15 MMAs per capsule, unrolled; +2 = second issuing warp, +4 = 8 warps of LDTM + FMA): issue %.1f clk/MMA, issue+retire %.1f clk/MMA%s\n", variant,
+    printf("mma3 variant %d (15 MMAs per capsule; 0 = every MMA re-reads the SAME 4 KB of A, 8 = A streams over 60 KB like the real tiles, +2 = second issuing warp): issue %.1f clk/MMA, issue+retire %.1f clk/MMA%s\n", variant,
            "", (double)h[0] / (15 * ncaps), (double)h[1] / (15 * ncaps));
   }
   CK(cudaFree(clk));

@@ -25,15 +25,15 @@
 extern "C" {
 #endif
 
-#define SRF_B200_VERSION 102 /* major*10000 + minor*100 + patch */
+#define SRF_B200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 typedef struct srf_handle srf_handle;
 
 /* u_hat arithmetic: how the prediction vectors W.x+b are formed (north_star knob). */
 enum {
   SRF_UHAT_FP32 = 0, /* FP32 FFMA on CUDA cores, fp32 weights                     */
-  SRF_UHAT_TF32 = 1, /* tensor cores, TF32 operands, fp32 accumulate (tcgen05)     */
-  SRF_UHAT_BF16 = 2, /* tensor cores, BF16 operands, fp32 accumulate (tcgen05)     */
+  SRF_UHAT_TF32 = 1, /* tensor cores, TF32 operands, fp32 accumulate (tcgen05); fused kernel: u_hat stays in TMEM */
+  SRF_UHAT_BF16 = 2, /* tensor cores, TF32 operands, fp32 accumulate, u_hat STORED as bf16 in HBM (two-kernel path) */
   SRF_UHAT_FP32X3 = 3 /* tensor cores, 3 x TF32 split (W_hi x_hi + W_lo x_hi + W_hi x_lo): fp32-class
                          u_hat (rel. error ~1e-6), fp32 storage -- the 1e-4 parity class on tcgen05 */
 };
@@ -95,6 +95,17 @@ int srf_destroy(srf_handle* h);
 /* last error message of this handle (host string, valid until the next call); h may be
  * NULL for errors of srf_create */
 const char* srf_last_error(const srf_handle* h);
+
+/*
+ * Kernel selection.  uhat_mode TF32 / FP32X3 run the FUSED routing kernel (routing_fused.cu: u_hat is
+ * produced by tcgen05.mma into TMEM and consumed there, an SDR stack is ONE persistent launch over all
+ * layers) when the shape is supported (d % 4 == 0, D <= 20, O <= 64, 16-byte aligned emb) and the
+ * library's policy expects it to be faster than the two-kernel path (materialised u_hat); BF16 always
+ * runs the two-kernel path, FP32 the CUDA-core kernel.  Results differ between the paths only within
+ * the mode's rounding class.  Environment (read by srf_create): SRF_NO_FUSED=1 / SRF_FORCE_FUSED=1.
+ * The fused kernel's waits are bounded: if one ever times out the launch drains and the NEXT call on
+ * the handle returns 700 + wait-site code ("a fused routing launch timed out ...").
+ */
 
 /* one routing layer, forward.  Replaces naive:145-191 (+193 when the head is requested). */
 int srf_route_layer_fwd(srf_handle* h, const srf_layer_desc* layer, void* stream);

@@ -1284,7 +1284,8 @@ size_t route_fused_smem_bytes(int OPL, int KC, int x3, int nwst, size_t wstage_b
 }
 
 template <int T4, int OPL, bool X3>
-static cudaError_t launch_fused_variant(const FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_fused_variant(const FusedParams& p, int grid, size_t smem, cudaStream_t stream,
+                                        const void* l2_window, size_t l2_window_bytes, float l2_hit_ratio) {
   auto kern = route_fused_kernel<T4, OPL, X3>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1293,11 +1294,20 @@ static cudaError_t launch_fused_variant(const FusedParams& p, int grid, size_t s
   cfg.blockDim = dim3(FZ_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on one another
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (l2_window && l2_window_bytes > 0) {
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(l2_window);
+    attr[1].val.accessPolicyWindow.num_bytes = l2_window_bytes;
+    attr[1].val.accessPolicyWindow.hitRatio = l2_hit_ratio;
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
@@ -1306,11 +1316,12 @@ bool route_fused_supported(int T4, int OPL) {
 }
 
 cudaError_t launch_route_fused(const FusedParams& p, int T4, int OPL, int x3, int grid, size_t smem,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, const void* l2_window, size_t l2_window_bytes,
+                               float l2_hit_ratio) {
 #define SRF_FUSED(T4_, OPL_)                                                              \
   if (T4 == T4_ && OPL == OPL_)                                                           \
-    return x3 ? launch_fused_variant<T4_, OPL_, true>(p, grid, smem, stream)              \
-              : launch_fused_variant<T4_, OPL_, false>(p, grid, smem, stream);
+    return x3 ? launch_fused_variant<T4_, OPL_, true>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio) \
+              : launch_fused_variant<T4_, OPL_, false>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio);
   SRF_FUSED(2, 1)
   SRF_FUSED(2, 2)
   SRF_FUSED(4, 1)

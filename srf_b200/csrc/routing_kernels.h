@@ -213,6 +213,7 @@ struct FusedParams {
   int layer_KX[FZ_MAX_LAYERS];
 };
 cudaError_t launch_route_fused(const FusedParams& p, int T4, int OPL, int x3, int grid, size_t smem,
-                               cudaStream_t stream);
+                               cudaStream_t stream, const void* l2_window, size_t l2_window_bytes,
+                               float l2_hit_ratio);
 }
 #endif

@@ -184,6 +184,66 @@ int srf_adam_step(srf_handle* h, float* param, const float* grad, float* m, floa
                   float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
 
 /*
+ * Capsulation front-end, forward (SURVEY.md 8f "next-1"): fbank features -> primary capsules, i.e.
+ * everything SequenceRouter.call does BEFORE the routing stack (naive:129-142):
+ *   CapsulationLayer (tfsr/model/sequence_router.py:44-82): 2 stages of { two Conv2D(3x3, stride 2,
+ *     padding 'same') paths -> Dropout(0.2) each -> maximum -> feat_mask -> BatchNormalization(axis=-1,
+ *     eps 1e-3) -> feat_mask }  (stage 0: Cin = 1, stage 1: Cin = C)
+ *   -> reshape [B,S,Fq*C] -> Dense(PH) "flatten" (naive:131-132)
+ *   [einsum variant only, pos_enc != 0: *= sqrt(PH); += get_pos_enc(S, PH)
+ *     (sequence_router_einsum.py:130-131, tfsr/helper/model_helper.py:30-58)]
+ *   -> two Conv2D(3x3, stride 1, 'same', 1 -> PD) "encaps" paths -> Dropout(0.2) -> maximum (naive:133)
+ *   -> feat_mask(stride^2) (naive:134) -> squash over PD (naive:137, :248-253)
+ *   -> LayerNormalization(PH*PD, eps 1e-3) "ln_input" (naive:139-141) -> Dropout(train_inp_dropout)
+ *     (naive:142) -> emb [B,S,PH,PD], the layout srf_route_stack_fwd reads.
+ * T1 = ceil(T/2), S = ceil(T1/2), F1 = ceil(F/2), Fq = ceil(F1/2) (TF 'same' padding: pad_total =
+ * max((out-1)*2 + 3 - in, 0), pad_before = pad_total / 2).  feat_mask zeroes the frames
+ * t >= ceil(length / stride^k) (model_helper.py:125-140).
+ *
+ * Kernels are TF layouts throughout: conv kernels [3,3,Cin,Cout], dense [Fq*C,PH].
+ * cnn_kernel[p][s]: path p (0/1) of stage s (the reference indexes conv_layers[p][s],
+ * sequence_router.py:76-77).
+ *
+ * training == 0: inference (Keras training=False): no dropout, BatchNormalization with the moving
+ *   statistics bn_mean / bn_var.
+ * training != 0: every non-NULL *_dropout tensor is an already scaled keep mask (0 or 1/(1-rate))
+ *   multiplied in where the reference applies the Dropout layer; BatchNormalization uses the batch
+ *   statistics over (B, time, freq) (biased variance) and updates bn_mean / bn_var IN PLACE with
+ *   momentum bn_momentum (moving = moving*m + batch*(1-m)).  Deterministic (no atomics).
+ * The backward of the front-end is not part of this library (tf.GradientTape / torch autograd
+ * differentiate the host-framework copy); out_emb feeds srf_route_stack_fwd directly.
+ */
+typedef struct srf_frontend_desc {
+  const float* feats;            /* [B,T,F] fbank features                                   */
+  const int32_t* lengths;        /* [B] int32 DEVICE: valid fbank frames per utterance       */
+  const float* cnn_kernel[2][2]; /* [path][stage] [3,3,Cin,C]                                */
+  const float* cnn_bias[2][2];   /* [path][stage] [C]                                        */
+  const float* bn_gamma[2];      /* [stage] [C]                                              */
+  const float* bn_beta[2];
+  float* bn_mean[2];             /* moving mean / variance (read; updated when training)     */
+  float* bn_var[2];
+  const float* dense_kernel;     /* [Fq*C,PH]                                                */
+  const float* dense_bias;       /* [PH]                                                     */
+  const float* encaps_kernel[2]; /* [path] [3,3,1,PD]                                        */
+  const float* encaps_bias[2];   /* [path] [PD]                                              */
+  const float* ln_gamma;         /* ln_input [PH*PD]                                         */
+  const float* ln_beta;
+  const float* cnn_dropout[2][2]; /* training: [path][stage] keep masks [B,T_s,F_s,C] or NULL */
+  const float* encaps_dropout[2]; /* training: [path] [B,S,PH,PD] or NULL                     */
+  const float* inp_dropout;       /* training: [B,S,PH,PD] or NULL                            */
+  float* out_emb;                /* [B,S,PH,PD]                                              */
+  int32_t B, T, F;               /* utterances, fbank frames, feature dim (123)              */
+  int32_t C;                     /* --model-conv-filter-num                                  */
+  int32_t PH, PD;                /* --model-caps-primary-num / -dim                          */
+  int32_t training;
+  int32_t pos_enc;               /* 1 = einsum variant's sqrt(PH) scale + positional encoding */
+  float bn_eps, bn_momentum;     /* Keras defaults 1e-3, 0.99                                */
+  float ln_eps, squash_eps;      /* 1e-3, 1e-7                                               */
+} srf_frontend_desc;
+
+int srf_capsulate_fwd(srf_handle* h, const srf_frontend_desc* fe, void* stream);
+
+/*
  * prediction vectors alone: window gather + u_hat = W.x + bias (naive:150-159) for every frame,
  * written in the reference's [B,S,I,O,D] layout (naive:158), fp32.  Uses emb, W, bias, B,S,H,d,
  * O,D, lpad, rpad and uhat_mode of the descriptor: SRF_UHAT_TF32 / SRF_UHAT_BF16 / SRF_UHAT_FP32X3

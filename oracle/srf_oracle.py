@@ -250,3 +250,82 @@ def greedy_ctc(logits: torch.Tensor, frame_lengths: Sequence[int]) -> List[List[
       prev = t
     out.append(seq)
   return out
+
+
+# --------------------------------------------------------------------------------------------
+# capsulation front-end (SURVEY.md 8f "next-1"): fbank -> primary capsules
+# --------------------------------------------------------------------------------------------
+def _conv2d_same(x: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor, stride: int) -> torch.Tensor:
+  """tf.keras.layers.Conv2D(padding='same') on NHWC with a [kh,kw,cin,cout] kernel:
+  out = ceil(in/stride), pad_total = max((out-1)*stride + k - in, 0), pad_before = pad_total // 2."""
+  B, H, W, _ = x.shape
+  k = kernel.shape[0]
+  oh, ow = -(-H // stride), -(-W // stride)
+  ph, pw = max((oh - 1) * stride + k - H, 0), max((ow - 1) * stride + k - W, 0)
+  xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+  y = torch.nn.functional.conv2d(xp, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=stride)
+  return y.permute(0, 2, 3, 1)
+
+
+def feat_mask(x: torch.Tensor, lengths: torch.Tensor, div: int) -> torch.Tensor:
+  """tfsr/helper/model_helper.py:125-140: frames at or beyond ceil(len / div) are zeroed."""
+  n = torch.ceil(lengths.to(torch.float64) / div).to(torch.int64)
+  mask = (torch.arange(x.shape[1])[None, :] < n[:, None]).to(x.dtype)
+  return x * mask[:, :, None, None]
+
+
+def pos_enc(length_: int, hidden: int) -> torch.Tensor:
+  """tfsr/helper/model_helper.py:30-58 (get_pos_enc; computed in float32 there)."""
+  nts = hidden // 2
+  inc = torch.tensor(math.log(1.0e4), dtype=torch.float32) / (torch.tensor(float(nts)) - 1)
+  inv = torch.exp(torch.arange(nts, dtype=torch.float32) * -inc)
+  st = torch.arange(length_, dtype=torch.float32)[:, None] * inv[None, :]
+  return torch.cat([torch.sin(st), torch.cos(st)], dim=1)
+
+
+def capsulate(feats: torch.Tensor, lengths, fe: dict, training: bool = False,
+              dropout: Optional[dict] = None, einsum_variant: bool = False, bn_momentum: float = 0.99,
+              bn_eps: float = 1e-3) -> Tuple[torch.Tensor, dict]:
+  """naive:129-142 with CapsulationLayer.call (tfsr/model/sequence_router.py:67-82):
+  fbank [B,T,F] -> primary capsules [B,S,PH,PD].  `fe`: parameters by the names of tests/golden
+  (TF layouts).  training=True: Keras BatchNormalization in training mode (batch statistics over
+  (B,time,freq), biased variance; returns the updated moving statistics) and the already scaled keep
+  masks of `dropout` ({"cnn<path>_<stage>", "encaps<path>", "inp"}) where the reference has Dropout
+  layers (sequence_router.py:60-61,76-77; naive:81-82,133,142).  einsum_variant: the sqrt(PH) scale and
+  positional encoding of sequence_router_einsum.py:130-131.
+  Returns (emb, {"bn<stage>_mean"/"bn<stage>_var": updated moving statistics})."""
+  dt = feats.dtype
+  f = {k: torch.as_tensor(v).to(dt) for k, v in fe.items()}
+  lens = torch.as_tensor(lengths)
+  dropout = dropout or {}
+  drop = lambda t, key: t * torch.as_tensor(dropout[key]).to(dt).reshape(t.shape) \
+      if (training and key in dropout) else t
+  moving = {}
+  x = feats[..., None]                                        # sequence_router.py:69
+  for st in range(2):                                         # sequence_router.py:71-81
+    x1 = drop(_conv2d_same(x, f["cnn0_%d_kernel" % st], f["cnn0_%d_bias" % st], 2), "cnn0_%d" % st)
+    x2 = drop(_conv2d_same(x, f["cnn1_%d_kernel" % st], f["cnn1_%d_bias" % st], 2), "cnn1_%d" % st)
+    x = torch.maximum(x1, x2)
+    x = feat_mask(x, lens, 2 ** (st + 1))
+    mean, var = f["bn%d_mean" % st], f["bn%d_var" % st]
+    if training:
+      bm, bv = x.mean(dim=(0, 1, 2)), x.var(dim=(0, 1, 2), unbiased=False)
+      moving["bn%d_mean" % st] = mean * bn_momentum + bm * (1 - bn_momentum)
+      moving["bn%d_var" % st] = var * bn_momentum + bv * (1 - bn_momentum)
+      mean, var = bm, bv
+    x = (x - mean) / torch.sqrt(var + bn_eps) * f["bn%d_gamma" % st] + f["bn%d_beta" % st]
+    x = feat_mask(x, lens, 2 ** (st + 1))
+  B, S = x.shape[0], x.shape[1]
+  emb = x.reshape(B, S, -1) @ f["dense_kernel"] + f["dense_bias"]      # naive:131-132
+  PH = emb.shape[-1]
+  if einsum_variant:                                                   # einsum:130-131
+    emb = emb * torch.sqrt(torch.tensor(float(PH), dtype=torch.float32)).to(dt) + pos_enc(S, PH).to(dt)
+  emb = emb[..., None]
+  emb = torch.maximum(drop(_conv2d_same(emb, f["encaps0_kernel"], f["encaps0_bias"], 1), "encaps0"),
+                      drop(_conv2d_same(emb, f["encaps1_kernel"], f["encaps1_bias"], 1), "encaps1"))  # naive:133
+  emb = feat_mask(emb, lens, 4)                                        # naive:134
+  emb = squash(emb, -1)                                                # naive:137
+  PD = emb.shape[-1]
+  flat = layer_norm(emb.reshape(B, S, PH * PD), f["ln_input_gamma"], f["ln_input_beta"])   # naive:139-141
+  emb = drop(flat.reshape(B, S, PH, PD), "inp")                        # naive:142
+  return emb, moving

@@ -16,7 +16,7 @@ UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF1
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",
            "srf_route_stack_fwd", "srf_route_layer_bwd", "srf_ctc_greedy_decode", "srf_ctc_loss",
-           "srf_adam_step", "srf_uhat_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
+           "srf_adam_step", "srf_uhat_fwd", "srf_capsulate_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
            "srf_last_kernel")
 
 
@@ -38,6 +38,24 @@ class LayerGrads(Structure):
   """struct srf_layer_grads (include/srf_b200.h)."""
   _fields_ = [(n, c_void_p) for n in ("v_raw", "d_out", "d_logits", "d_raw", "dW", "dbias", "dgamma",
                                       "dbeta", "dhead_gamma", "dhead_beta", "d_emb")]
+
+
+class FrontendDesc(Structure):
+  """struct srf_frontend_desc (include/srf_b200.h)."""
+  _fields_ = [
+      ("feats", c_void_p), ("lengths", c_void_p),
+      ("cnn_kernel", (c_void_p * 2) * 2), ("cnn_bias", (c_void_p * 2) * 2),
+      ("bn_gamma", c_void_p * 2), ("bn_beta", c_void_p * 2), ("bn_mean", c_void_p * 2),
+      ("bn_var", c_void_p * 2),
+      ("dense_kernel", c_void_p), ("dense_bias", c_void_p),
+      ("encaps_kernel", c_void_p * 2), ("encaps_bias", c_void_p * 2),
+      ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
+      ("cnn_dropout", (c_void_p * 2) * 2), ("encaps_dropout", c_void_p * 2), ("inp_dropout", c_void_p),
+      ("out_emb", c_void_p),
+      ("B", c_int32), ("T", c_int32), ("F", c_int32), ("C", c_int32), ("PH", c_int32), ("PD", c_int32),
+      ("training", c_int32), ("pos_enc", c_int32),
+      ("bn_eps", c_float), ("bn_momentum", c_float), ("ln_eps", c_float), ("squash_eps", c_float),
+  ]
 
 
 _lib = None
@@ -76,6 +94,8 @@ def load() -> ctypes.CDLL:
   lib.srf_adam_step.restype = c_int
   lib.srf_uhat_fwd.argtypes = [c_void_p, POINTER(LayerDesc), c_void_p, c_void_p]
   lib.srf_uhat_fwd.restype = c_int
+  lib.srf_capsulate_fwd.argtypes = [c_void_p, POINTER(FrontendDesc), c_void_p]
+  lib.srf_capsulate_fwd.restype = c_int
   lib.srf_profile_begin.argtypes = [c_void_p]
   lib.srf_profile_begin.restype = c_int
   lib.srf_profile_end.argtypes = [c_void_p, POINTER(c_float), POINTER(c_int32)]

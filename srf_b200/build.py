@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsrf_b200.so")
 STAMP = os.path.join(HERE, ".libsrf_b200.stamp")
 SOURCES = ["capi.cu", "routing_fwd.cu", "uhat_gemm.cu", "routing_stream.cu", "routing_fused.cu",
-           "routing_bwd.cu", "ctc_adam.cu"]
+           "routing_bwd.cu", "ctc_adam.cu", "frontend.cu"]
 HEADERS = ["routing_kernels.h", "sm100_ptx.cuh", os.path.join("..", "..", "include", "srf_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -45,6 +45,8 @@ struct srf_handle {
   int bwd_atomics = 0;
   float* ctc_ws = nullptr;  // alpha workspace of srf_ctc_loss
   size_t ctc_ws_bytes = 0;
+  float* fe_ws = nullptr;   // front-end intermediates of srf_capsulate_fwd
+  size_t fe_ws_bytes = 0;
   unsigned long long* dbg = nullptr;  // SRF_PHASE_TIMERS=1: per-CTA phase timers of the streaming kernel
   // tensor-core path
   std::vector<PackedWeights> packed_mma;
@@ -207,6 +209,7 @@ extern "C" int srf_destroy(srf_handle* h) {
   if (h->fz_host_abort) cudaFreeHost(h->fz_host_abort);
   if (h->dbg) cudaFree(h->dbg);
   if (h->ctc_ws) cudaFree(h->ctc_ws);
+  if (h->fe_ws) cudaFree(h->fe_ws);
   if (h->bwd_ws) cudaFree(h->bwd_ws);
   for (int i = 0; i < 2; ++i)
     if (h->ws[i]) cudaFree(h->ws[i]);
@@ -272,6 +275,48 @@ extern "C" int srf_adam_step(srf_handle* h, float* param, const float* grad, flo
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, "adam launch");
+  return 0;
+}
+
+extern "C" int srf_capsulate_fwd(srf_handle* h, const srf_frontend_desc* fe, void* stream_) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (!fe) return fail(h, -1, "front-end descriptor is NULL");
+  const srf_frontend_desc& d = *fe;
+  if (d.B == 0) return 0;
+  if (d.B < 0 || d.T <= 0 || d.F <= 0 || d.C <= 0 || d.PH <= 0 || d.PD <= 0)
+    return fail(h, -2, "front-end: bad shape (B=%d T=%d F=%d C=%d PH=%d PD=%d)", d.B, d.T, d.F, d.C, d.PH, d.PD);
+  if (!d.feats || !d.lengths || !d.out_emb || !d.dense_kernel || !d.dense_bias || !d.ln_gamma || !d.ln_beta)
+    return fail(h, -1, "front-end: NULL argument");
+  for (int a = 0; a < 2; ++a) {
+    if (!d.encaps_kernel[a] || !d.encaps_bias[a] || !d.bn_gamma[a] || !d.bn_beta[a] || !d.bn_mean[a] ||
+        !d.bn_var[a])
+      return fail(h, -1, "front-end: NULL argument");
+    for (int b = 0; b < 2; ++b)
+      if (!d.cnn_kernel[a][b] || !d.cnn_bias[a][b]) return fail(h, -1, "front-end: NULL argument");
+  }
+  if (d.pos_enc && (d.PH & 1))
+    return fail(h, -2, "front-end: the positional encoding needs an even model_caps_primary_num");
+  DeviceGuard g(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t need = srf::frontend_workspace_bytes(d);
+  if (need > h->fe_ws_bytes) {
+    if (h->fe_ws) cudaFreeAsync(h->fe_ws, stream);
+    h->fe_ws = nullptr;
+    h->fe_ws_bytes = 0;
+    cudaError_t e = cudaMallocAsync((void**)&h->fe_ws, need, stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "front-end workspace allocation");
+    h->fe_ws_bytes = need;
+  }
+  int launches = 0;
+  const char* why = "";
+  cudaError_t e = srf::launch_frontend(d, h->fe_ws, h->max_smem, stream, &launches, &why);
+  h->launches += launches;
+  if (e == cudaErrorInvalidValue && why[0]) {
+    cudaGetLastError();
+    return fail(h, -3, "front-end: %s", why);
+  }
+  if (e != cudaSuccess) return cuda_fail(h, e, "front-end launch");
+  h->last_kernel = "fe_conv_maxout_kernel x2 + fe_dense_kernel + fe_encaps_kernel";
   return 0;
 }
 

@@ -8,6 +8,8 @@
 #define SRF_NW 8  // warps per CTA of the fused FP32 layer kernel
 #endif
 
+struct srf_frontend_desc;
+
 namespace srf {
 
 struct RouteParams {
@@ -145,6 +147,13 @@ void launch_pack_weights_fused(const float* W, const float* bias, float* Wf, int
 bool route_fused_supported(int T4, int OPL);
 size_t route_fused_smem_bytes(int OPL, int KC, int x3, int nwst, size_t wstage_bytes);
 
+}  // namespace srf
+
+// capsulation front-end (frontend.cu)
+namespace srf {
+size_t frontend_workspace_bytes(const srf_frontend_desc& d);
+cudaError_t launch_frontend(const srf_frontend_desc& d, float* ws, int max_smem, cudaStream_t stream,
+                            int* launches, const char** why);
 }  // namespace srf
 
 // needs <cuda.h> for CUtensorMap; declared separately so plain users of this header need not include it

@@ -301,3 +301,81 @@ def route_layer_bwd(emb, args: LayerArgs, v_raw, d_out=None, d_logits=None, need
   rc = h.lib.srf_route_layer_bwd(h._h, ctypes.byref(desc), ctypes.byref(gr), stream)
   _lib.check(h.lib, h._h, rc, "srf_route_layer_bwd")
   return g
+
+
+def capsulate_fwd(feats, lengths, fe: dict, C: int, PH: int, PD: int, training: bool = False,
+                  dropout: Optional[dict] = None, pos_enc: bool = False,
+                  handle: Optional[Handle] = None) -> torch.Tensor:
+  """Capsulation front-end, forward (srf_capsulate_fwd; naive:129-142, sequence_router.py:44-82):
+  fbank [B,T,F] + lengths [B] -> primary capsules emb [B,S,PH,PD].  `fe`: front-end parameters by
+  the names of tests/golden (TF layouts, device tensors).  training=True: BatchNormalization with
+  batch statistics (fe["bn*_mean"/"bn*_var"] are updated in place) and the keep masks of
+  `dropout` ({"cnn<path>_<stage>", "encaps<path>", "inp"} -> already scaled mask) are applied."""
+  feats = as_device_tensor(feats)
+  if feats.dim() != 3:
+    raise ValueError("feats must be [B,T,F], got %s" % (tuple(feats.shape),))
+  dev = feats.device
+  h = handle or default_handle(dev)
+  B, T, F = feats.shape
+  S = -(-(-(-T // 2)) // 2)
+  lens = torch.as_tensor(lengths).to(device=dev, dtype=torch.int32).contiguous()
+  if lens.numel() != B:
+    raise ValueError("input_lengths has %d entries for %d utterances" % (lens.numel(), B))
+  keep = [feats, lens]
+
+  def par(name, numel=None):
+    if name not in fe:
+      raise ValueError("front-end parameter %r is missing" % name)
+    t = as_device_tensor(fe[name], dev)
+    if numel is not None and t.numel() != numel:
+      raise ValueError("front-end parameter %s has %d elements, expected %d" % (name, t.numel(), numel))
+    keep.append(t)
+    return t.data_ptr()
+
+  F1 = -(-F // 2)
+  Fq = -(-F1 // 2)
+  d = _lib.FrontendDesc()
+  d.feats, d.lengths = feats.data_ptr(), lens.data_ptr()
+  for p_ in range(2):
+    for st in range(2):
+      cin = 1 if st == 0 else C
+      d.cnn_kernel[p_][st] = par("cnn%d_%d_kernel" % (p_, st), 9 * cin * C)
+      d.cnn_bias[p_][st] = par("cnn%d_%d_bias" % (p_, st), C)
+    d.encaps_kernel[p_] = par("encaps%d_kernel" % p_, 9 * PD)
+    d.encaps_bias[p_] = par("encaps%d_bias" % p_, PD)
+  for st in range(2):
+    d.bn_gamma[st], d.bn_beta[st] = par("bn%d_gamma" % st, C), par("bn%d_beta" % st, C)
+    if training and not fe["bn%d_mean" % st].is_contiguous():
+      raise ValueError("BatchNormalization moving statistics must be contiguous (updated in place)")
+    d.bn_mean[st], d.bn_var[st] = par("bn%d_mean" % st, C), par("bn%d_var" % st, C)
+  d.dense_kernel, d.dense_bias = par("dense_kernel", Fq * C * PH), par("dense_bias", PH)
+  d.ln_gamma, d.ln_beta = par("ln_input_gamma", PH * PD), par("ln_input_beta", PH * PD)
+  if training and dropout:
+    T1 = -(-T // 2)
+    shp = {0: B * T1 * F1 * C, 1: B * S * Fq * C}
+    for key, m in dropout.items():
+      m = as_device_tensor(m, dev)
+      keep.append(m)
+      if key == "inp":
+        want = B * S * PH * PD
+        d.inp_dropout = m.data_ptr()
+      elif key.startswith("encaps"):
+        want = B * S * PH * PD
+        d.encaps_dropout[int(key[6:])] = m.data_ptr()
+      elif key.startswith("cnn"):
+        p_, st = int(key[3]), int(key[5])
+        want = shp[st]
+        d.cnn_dropout[p_][st] = m.data_ptr()
+      else:
+        raise ValueError("unknown dropout mask %r" % key)
+      if m.numel() != want:
+        raise ValueError("dropout mask %s has %d elements, expected %d" % (key, m.numel(), want))
+  emb = torch.empty((B, S, PH, PD), dtype=torch.float32, device=dev)
+  d.out_emb = emb.data_ptr()
+  d.B, d.T, d.F, d.C, d.PH, d.PD = B, T, F, C, PH, PD
+  d.training, d.pos_enc = int(bool(training)), int(bool(pos_enc))
+  d.bn_eps, d.bn_momentum, d.ln_eps, d.squash_eps = 1e-3, 0.99, LN_EPS, 1e-7
+  stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  rc = h.lib.srf_capsulate_fwd(h._h, ctypes.byref(d), stream)
+  _lib.check(h.lib, h._h, rc, "srf_capsulate_fwd")
+  return emb

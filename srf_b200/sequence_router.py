@@ -200,6 +200,16 @@ def _conv2d_same_nhwc(x, kernel, bias, stride):
   return y.permute(0, 2, 3, 1)
 
 
+def _pos_enc(length, hidden, device):
+  """tfsr/helper/model_helper.py:30-58 (float32 throughout)."""
+  import math
+  nts = hidden // 2
+  inc = torch.tensor(math.log(1.0e4), dtype=torch.float32) / (torch.tensor(float(nts)) - 1)
+  inv = torch.exp(torch.arange(nts, dtype=torch.float32) * -inc)
+  st = torch.arange(length, dtype=torch.float32)[:, None] * inv[None, :]
+  return torch.cat([torch.sin(st), torch.cos(st)], dim=1).to(device)
+
+
 def _feat_mask(x, lengths, div):
   """tfsr/helper/model_helper.py:125-140: zero the frames at or beyond ceil(len / div)."""
   n = torch.ceil(lengths.to(torch.float32) / div).to(torch.int64)
@@ -220,10 +230,16 @@ class SequenceRouter:
   path.
   """
 
-  def __init__(self, config, logger, class_n, device=None, seed=None, uhat_mode="exact"):
+  def __init__(self, config, logger, class_n, device=None, seed=None, uhat_mode="exact", caps_type=None):
     self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
     import math
+    # --model-caps-type (tfsr/trainer_sr.py:188-199): "naive" and "lowmemory" compute the same function;
+    # "einsum" scales the projected frame by sqrt(PH), adds the positional encoding
+    # (sequence_router_einsum.py:130-131) and uses 1e-9 inside the head's length (einsum:238)
+    self.caps_type = caps_type or getattr(config, "model_caps_type", None) or "naive"
+    if self.caps_type not in ("naive", "lowmemory", "einsum"):
+      raise ValueError("model_caps_type must be naive, lowmemory or einsum, got %r" % (self.caps_type,))
     self.stride = 2
     self.cnn_n = config.model_conv_layer_num
     self.feat_dim = math.ceil(config.feat_dim / (self.stride * self.cnn_n))   # naive:50
@@ -239,7 +255,7 @@ class SequenceRouter:
         config.model_caps_primary_dim, config.model_caps_convolution_dim, config.model_caps_class_dim,
         self.lpad, self.rpad, self.iter, self.is_context,
         inn_dropout=getattr(config, "train_inn_dropout", 0.1), device=self.device, seed=seed,
-        uhat_mode=uhat_mode)
+        uhat_mode=uhat_mode, length_eps=1e-9 if self.caps_type == "einsum" else routing.LENGTH_EPS)
     self.inp_dropout = float(getattr(config, "train_inp_dropout", 0.1))
     self.fe = {}   # front-end parameters, TF layouts; filled by load_frontend / first call
     self._fe_seed = seed
@@ -302,11 +318,28 @@ class SequenceRouter:
     return [v for _, v in self.named_parameters()]
 
   # -- forward ---------------------------------------------------------------------------
-  def capsulate(self, inputs, input_lengths, training: bool = False):
-    """fbank [B,T,feat] -> primary capsules emb [B,S,PH,PD] (naive:129-142).  training=True:
+  def capsulate(self, inputs, input_lengths, training: bool = False, dropout: Optional[dict] = None):
+    """fbank [B,T,feat] -> primary capsules emb [B,S,PH,PD] (naive:129-142) in the CUDA library
+    (srf_capsulate_fwd: no framework op between the features and the routing stack).
+    training=True: BatchNormalization with batch statistics + moving-average update, and the keep
+    masks in `dropout` (routing.capsulate_fwd) where the reference has Dropout layers; forward only
+    -- the differentiable training path is `capsulate_autograd`."""
+    x = routing_as_tensor(inputs, self.device)
+    if not self.fe:
+      self._init_frontend(x.shape[-1])
+    if self.cnn_n != 2:
+      raise ValueError("the reference's CapsulationLayer only works with model_conv_layer_num == 2 "
+                       "(sequence_router.py:52-63,76-77)")
+    return routing.capsulate_fwd(x, input_lengths, self.fe, self.nfilt, self.caps_inp_n, self.caps_inp_d,
+                                 training=training, dropout=dropout, pos_enc=self.caps_type == "einsum",
+                                 handle=self.stack.handle)
+
+  def capsulate_autograd(self, inputs, input_lengths, training: bool = False):
+    """The same front-end as differentiable torch ops, for training through torch autograd
+    (tfsr/trainer_sr.py:62-71 differentiates it with tf.GradientTape).  training=True:
     Dropout(0.2) after every front-end convolution (sequence_router.py:60-61,76-77; naive:81-82,
     132), BatchNormalization with batch statistics and moving-average update (momentum 0.99),
-    input dropout `train_inp_dropout` (naive:142); all torch ops, differentiable."""
+    input dropout `train_inp_dropout` (naive:142)."""
     import torch.nn.functional as F
     x = routing_as_tensor(inputs, self.device)
     lens = torch.as_tensor(input_lengths).to(self.device)
@@ -332,6 +365,8 @@ class SequenceRouter:
       x = _feat_mask(x, lens, self.stride ** (li + 1))
     B, S = x.shape[0], x.shape[1]
     emb = x.reshape(B, S, self.feat_dim * self.nfilt) @ f["dense_kernel"] + f["dense_bias"]
+    if self.caps_type == "einsum":                     # einsum:130-131
+      emb = emb * float(self.caps_inp_n) ** 0.5 + _pos_enc(S, self.caps_inp_n, emb.device)
     emb = emb[..., None]                               # [B,S,PH,1]
     emb = torch.maximum(drop(_conv2d_same_nhwc(emb, f["encaps0_kernel"], f["encaps0_bias"], 1)),
                         drop(_conv2d_same_nhwc(emb, f["encaps1_kernel"], f["encaps1_bias"], 1)))
@@ -367,7 +402,7 @@ class SequenceRouter:
       raise ValueError("input_lengths is required (naive:121)")
     if training:
       from . import autograd
-      emb = self.capsulate(inputs, input_lengths, training=True)
+      emb = self.capsulate_autograd(inputs, input_lengths, training=True)
       return autograd.route_stack(self.stack, emb)
     with torch.no_grad():
       emb = self.capsulate(inputs, input_lengths)

@@ -51,6 +51,23 @@ def test_layer_desc_matches_header_layout():
   assert ctypes.sizeof(_lib.LayerDesc) == 11 * 8 + 12 * 4 + 2 * 4 + 8
 
 
+def test_frontend_desc_matches_header_layout():
+  from srf_b200 import _lib
+  with open(os.path.join(ROOT, "include", "srf_b200.h")) as f:
+    text = f.read()
+  body = re.search(r"typedef struct srf_frontend_desc \{(.*?)\} srf_frontend_desc;", text, re.S).group(1)
+  body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+  fields = []
+  for decl in body.split(";"):
+    for part in decl.split(","):
+      part = re.sub(r"\[\d+\]", "", part.replace("*", " ")).strip()
+      if part:
+        fields.append(part.split()[-1])
+  assert fields == [n for n, _ in _lib.FrontendDesc._fields_]
+  # 34 pointers + 8 int32 + 4 float
+  assert ctypes.sizeof(_lib.FrontendDesc) == 34 * 8 + 8 * 4 + 4 * 4
+
+
 def test_no_gpu_means_loud_failure(built_lib):
   import pytest
   import torch

@@ -40,3 +40,17 @@ def test_oracle_fp32_within_tolerance_of_reference_fp32_run(name):
   lens = [int(n) // 4 for n in g["input_lengths"]]
   assert o.greedy_ctc(logits, lens) == o.greedy_ctc(ref, lens)
   assert o.greedy_ctc(g["logits_f32"], lens) == o.greedy_ctc(ref, lens)
+
+
+@pytest.mark.parametrize("name", gu.golden_names())
+def test_oracle_frontend_matches_reference_code(name):
+  """The front-end restatement (oracle.capsulate, naive:129-142) against the primary capsules the
+  reference's own file produced from the same fbank input and front-end parameters."""
+  g = gu.load(name)
+  z = g["raw"]
+  fe = {n[3:]: z[n] for n in z.files if n.startswith("fe_")}
+  # the emulation runs the front-end's Dropout / BatchNormalization layers in inference mode even
+  # for the training golden (only the routing stack's masks are injected there)
+  emb, _ = o.capsulate(torch.from_numpy(z["feats"]).double(), z["input_lengths"], fe)
+  assert emb.shape == g["emb"].shape
+  assert (emb - g["emb"]).abs().max().item() < 1e-10

@@ -174,10 +174,26 @@ UHAT_DESC = {
     "fp32": "FP32 CUDA cores, fused FP32 kernel",
     "tf32": "fused routing kernel: tcgen05 TF32 MMA into TMEM, u_hat consumed in place (never in HBM), "
             "SDR stack as one layer-wavefront launch (1e-2 tolerance class, identical greedy CTC)",
+    "f16": "fused routing kernel: tcgen05 kind::f16 MMA on FP16 operand images (the 11-bit significand of TF32, "
+           "2/3 of its operand bytes at d=20) into TMEM, u_hat consumed in place (never in HBM), SDR stack as one "
+           "layer-wavefront launch (1e-2 tolerance class, identical greedy CTC)",
     "bf16": "two kernels: tcgen05 TF32 MMA, bf16 u_hat materialised in HBM, streaming routing kernel",
     "fp32x3": "3 x TF32 split (fp32-class u_hat, 1e-4 tolerance class); fused kernel or two-kernel path "
               "by the library's policy",
 }
+
+
+def packed_weight_bytes(w, uhat):
+  """Bytes of the fused kernel's packed operand images (one pass over all layers): per input capsule
+  32 * ceil(O/32) * 4 * ceil(D/4) rows of KC 16-byte chunks (csrc/capi.cu fused_geometry)."""
+  total = 0
+  for (I, O, D, d) in shapes_of(w):
+    t4 = (D + 3) // 4
+    t4 = 2 if t4 <= 2 else (4 if t4 <= 4 else 5)
+    rows = 32 * ((O + 31) // 32) * 4 * t4
+    kc = 2 * ((d + 1 + 15) // 16) if uhat == "f16" else 2 * ((d + 1 + 7) // 8)
+    total += I * rows * kc * 16 * (2 if uhat == "fp32x3" else 1)
+  return total
 
 
 def main():
@@ -189,8 +205,9 @@ def main():
   ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-also", action="store_true", help="skip the strong-scaling, training and other-config legs")
-  ap.add_argument("--uhat", default="tf32", choices=["fp32", "tf32", "bf16", "fp32x3"],
-                  help="u_hat arithmetic: tf32 = fused tcgen05 kernel (default), fp32x3 = the 1e-4 class, "
+  ap.add_argument("--uhat", default="f16", choices=["fp32", "tf32", "f16", "bf16", "fp32x3"],
+                  help="u_hat arithmetic: f16 = fused tcgen05 kernel on FP16 operand images (default), tf32 = the "
+                       "same kernel on TF32 operands, fp32x3 = the 1e-4 class, "
                        "bf16 = round-1 two-kernel path with bf16 u_hat in HBM, fp32 = CUDA-core kernel")
   args = ap.parse_args()
   w = dict(WORKLOADS[args.workload])
@@ -304,7 +321,9 @@ def main():
   fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
   # the fused roofline: t_roof = max(tensor time of the u_hat contraction, HBM time
   # of the algorithmic bytes); the dense contraction binds for every config of BASELINE.json
-  t_tensor = f_uhat * frames_rank / (p_tf32 * 1e12)
+  # tensor peak of the mode's MMA kind: kind::f16 runs at the measured bf16/fp16 rate, kind::tf32 at half
+  p_tensor = p_bf16 if args.uhat == "f16" else p_tf32
+  t_tensor = f_uhat * frames_rank / (p_tensor * 1e12)
   t_hbm = (bytes_frame * frames_rank + weights) / (p_hbm * 1e9)
   t_roof = max(t_tensor, t_hbm)
   kernel_ms = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
@@ -325,12 +344,16 @@ def main():
   achieved = f_uhat * frames_rank / share / (dom_ms_launch / 1e3) / 1e12
   uhat_elems = sum(I * O * D for (I, O, D, d) in shapes_of(w))          # per routing frame, all layers
   roofline = {
-      "bound": "tensor" if t_tensor >= t_hbm else "hbm", "achieved": achieved, "peak": p_tf32, "unit": "TFLOP/s",
-      "frac": achieved / p_tf32, "traffic": traffic,
+      "bound": "tensor" if t_tensor >= t_hbm else "hbm", "achieved": achieved, "peak": p_tensor, "unit": "TFLOP/s",
+      "frac": achieved / p_tensor, "traffic": traffic,
+      "frac_vs_bf16_peak": achieved / p_bf16, "frac_vs_derived_tf32_peak": achieved / p_tf32,
       "note": "dominant kernel %s (%d launch(es) per step); achieved = algorithmic u_hat FLOPs (2 I O D d per "
-              "frame-layer, SURVEY.md 8d) per launch / CUDA-event launch time; peak = TF32 derived as half the "
-              "measured sustained bf16 GEMM rate" % ("route_fused_kernel" if fused else dom, round(share)),
-      "peak_source": peak_src + " (bf16 sustained / 2: derived TF32)", "kernel": kernel_name, "dominant": dom,
+              "frame-layer, SURVEY.md 8d) per launch / CUDA-event launch time; peak = %s"
+              % ("route_fused_kernel" if fused else dom, round(share),
+                 "the measured sustained bf16 GEMM rate (kind::f16 MMA)" if args.uhat == "f16" else
+                 "TF32 derived as half the measured sustained bf16 GEMM rate"),
+      "peak_source": peak_src + (" (bf16 sustained: the kind::f16 rate)" if args.uhat == "f16" else
+                                 " (bf16 sustained / 2: derived TF32)"), "kernel": kernel_name, "dominant": dom,
       "launch_ms": dom_ms_launch, "kernel_ms": kernel_ms,
       "fused_roofline_frac": t_roof / (ms_step / 1e3),
       "hbm_frac_fused_min": (bytes_frame * frames_rank + weights) / (ms_step / 1e3) / 1e9 / p_hbm,
@@ -340,18 +363,19 @@ def main():
     # what actually bounds the fused kernel: every time step re-streams the layer's weights from L2
     # into shared memory (measured bulk-copy ingest 60-70 B/clk/SM = 17-19 TB/s, profiles/r2_ubench.txt)
     groups = (B + 31) // 32
-    w_bytes_step = groups * S * weights * (2 if args.uhat == "fp32x3" else 1) * (32.0 / 30.0)
+    w_bytes_step = groups * S * packed_weight_bytes(w, args.uhat)
     roofline["l2_weight_stream"] = {"bytes_per_step": w_bytes_step, "achieved_gbs": w_bytes_step / (ms_step / 1e3) / 1e9,
                                     "measured_l2_to_smem_gbs": 17400.0}
   else:
-    esize = {"fp32": 0, "tf32": 4, "bf16": 2, "fp32x3": 4}[args.uhat]
+    esize = {"fp32": 0, "tf32": 4, "f16": 4, "bf16": 2, "fp32x3": 4}[args.uhat]
     roofline["materialised_uhat_gbs"] = (uhat_elems * esize * frames_rank / n_layers + bytes_frame * frames_rank / n_layers) / (dom_ms_launch / 1e3) / 1e9
 
   line = {
       "metric": "routing_frames_per_sec", "value": value, "unit": "routing frames/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-      "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "fp32x3": "f32"}[args.uhat], "data": "synthetic",
+      "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16", "bf16": "bf16", "fp32x3": "f32"}[args.uhat],
+      "data": "synthetic",
       "config": {"workload": w["desc"], "global_batch": B * world, "routing_frames_per_utt": S,
                  "fbank_frames_per_sec": value * 4, "uhat": UHAT_DESC[args.uhat],
                  "parallelism": "dp%d: every GPU routes its own 64 utterances, no collective (weak); the sharded "
@@ -384,7 +408,7 @@ def main():
     from srf_b200 import training
     w4 = WORKLOADS["cfg3"]
     B4, S4 = max(1, 64 // world), (w4["T"] + 3) // 4
-    train_mode = "bf16" if args.uhat in ("tf32", "bf16") else args.uhat
+    train_mode = "bf16" if args.uhat in ("tf32", "f16", "bf16") else args.uhat
     st4 = build_stack(w4, dev, train_mode)
     tr4 = training.TrainStep(st4, B4 * world)
     g4 = torch.Generator().manual_seed(4 + rank)

@@ -34,8 +34,14 @@ enum {
   SRF_UHAT_FP32 = 0, /* FP32 FFMA on CUDA cores, fp32 weights                     */
   SRF_UHAT_TF32 = 1, /* tensor cores, TF32 operands, fp32 accumulate (tcgen05); fused kernel: u_hat stays in TMEM */
   SRF_UHAT_BF16 = 2, /* tensor cores, TF32 operands, fp32 accumulate, u_hat STORED as bf16 in HBM (two-kernel path) */
-  SRF_UHAT_FP32X3 = 3 /* tensor cores, 3 x TF32 split (W_hi x_hi + W_lo x_hi + W_hi x_lo): fp32-class
+  SRF_UHAT_FP32X3 = 3, /* tensor cores, 3 x TF32 split (W_hi x_hi + W_lo x_hi + W_hi x_lo): fp32-class
                          u_hat (rel. error ~1e-6), fp32 storage -- the 1e-4 parity class on tcgen05 */
+  SRF_UHAT_F16 = 4    /* tensor cores, FP16 operand images (kind::f16), fp32 accumulate, fused kernel.  FP16
+                         carries the same 11-bit significand as TF32, so the rounding class is that of
+                         SRF_UHAT_TF32, with 2/3 (d = 20) to 1/2 (d = 8, 16) of the operand bytes streamed
+                         per time step; operands are clamped to the finite FP16 range (|x|, |W| <= 65504;
+                         magnitudes below 6.1e-5 keep an absolute error <= 3e-8).  Shapes the fused kernel
+                         does not take run as SRF_UHAT_TF32 */
 };
 
 /*

@@ -9,9 +9,9 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrf_b200.so")
 
-SRF_UHAT_FP32, SRF_UHAT_TF32, SRF_UHAT_BF16, SRF_UHAT_FP32X3 = 0, 1, 2, 3
+SRF_UHAT_FP32, SRF_UHAT_TF32, SRF_UHAT_BF16, SRF_UHAT_FP32X3, SRF_UHAT_F16 = 0, 1, 2, 3, 4
 UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF16,
-              "fp32x3": SRF_UHAT_FP32X3}
+              "fp32x3": SRF_UHAT_FP32X3, "f16": SRF_UHAT_F16}
 
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",

@@ -13,8 +13,11 @@ Reference behaviour mirrored here:
     `max_to_keep < 0` keeps everything.
   * checkpoint averaging (tfsr/utils/average_ckpt_sr.py:100-179): element-wise mean of the
     weights of the last `model_average_num` checkpoints, written to `<path_ckpt>/avg`.
-TensorFlow's checkpoint container cannot be read here (no TF); checkpoints are `.npz` files with
-the same variable names.
+Two containers: `.npz` files with the same variable names (`ckpt-<epoch>.npz`), and TensorFlow's own
+tensor-bundle container (`ckpt-<epoch>.index` + `.data-00000-of-00001`, object-based variable names
+`model/wgt/0/.ATTRIBUTES/VARIABLE_VALUE` ...) read and written without TensorFlow by
+`srf_b200.tf_bundle` -- so checkpoints trained with the reference load here, and checkpoints saved
+with `fmt="tf"` restore in the reference (`ckpt.restore(path).expect_partial()`).
 """
 from __future__ import annotations
 
@@ -133,13 +136,26 @@ def _ckpt_path(path_ckpt: str, epoch: int) -> str:
 
 
 def list_checkpoints(path_ckpt: str) -> List[Tuple[int, str]]:
-  """(epoch, path) sorted by epoch."""
-  out = []
+  """(epoch, path) sorted by epoch; `.npz` files and TensorFlow bundles (`ckpt-<n>.index`, returned
+  as the bundle prefix `.../ckpt-<n>`).  When both exist for an epoch the `.npz` wins."""
+  found = {}
+  for p in glob.glob(os.path.join(path_ckpt, "ckpt-*.index")):
+    m = re.fullmatch(r"ckpt-(\d+)\.index", os.path.basename(p))
+    if m:
+      found[int(m.group(1))] = p[:-len(".index")]
   for p in glob.glob(os.path.join(path_ckpt, "ckpt-*.npz")):
     m = re.fullmatch(r"ckpt-(\d+)\.npz", os.path.basename(p))
     if m:
-      out.append((int(m.group(1)), p))
-  return sorted(out)
+      found[int(m.group(1))] = p
+  return sorted(found.items())
+
+
+def _remove_checkpoint(path: str) -> None:
+  if path.endswith(".npz"):
+    os.remove(path)
+    return
+  for p in glob.glob(path + ".index") + glob.glob(path + ".data-*"):
+    os.remove(p)
 
 
 def latest_checkpoint(path_ckpt: str) -> Optional[str]:
@@ -148,9 +164,15 @@ def latest_checkpoint(path_ckpt: str) -> Optional[str]:
 
 
 def save_checkpoint(state: Dict[str, np.ndarray], path_ckpt: str, epoch: int,
-                    max_to_keep: int = -1, variant: Optional[str] = None) -> str:
-  """Write `ckpt-<epoch>.npz`; keep the newest `max_to_keep` files (< 0: keep all,
-  misc_helper.py:143-145).  With `variant`, routing weights are stored in that reference layout."""
+                    max_to_keep: int = -1, variant: Optional[str] = None, fmt: str = "npz") -> str:
+  """Write `ckpt-<epoch>.npz` (fmt="npz") or a TensorFlow tensor bundle `ckpt-<epoch>.index/.data-*`
+  with the reference's object-based variable names (fmt="tf"; `variant` defaults to "naive" there);
+  keep the newest `max_to_keep` checkpoints (< 0: keep all, misc_helper.py:143-145).  With `variant`,
+  routing weights are stored in that reference layout."""
+  if fmt not in ("npz", "tf"):
+    raise ValueError("fmt must be 'npz' or 'tf'")
+  if fmt == "tf" and variant is None:
+    variant = "naive"
   os.makedirs(path_ckpt, exist_ok=True)
   out = {}
   for name, arr in state.items():
@@ -159,20 +181,33 @@ def save_checkpoint(state: Dict[str, np.ndarray], path_ckpt: str, epoch: int,
     idx = sorted(int(n[1:]) for n in out if re.fullmatch(r"W\d+", n))
     for i in idx:
       out["W%d" % i], out["b%d" % i] = from_canonical(*to_canonical(out["W%d" % i], out["b%d" % i]), variant)
-  path = _ckpt_path(path_ckpt, epoch)
-  tmp = path + ".tmp.npz"
-  np.savez(tmp, **out)
-  os.replace(tmp, path)
+  if fmt == "tf":
+    from . import tf_bundle
+    path = tf_bundle.write_reference_checkpoint(path_ckpt, epoch, out)
+  else:
+    path = _ckpt_path(path_ckpt, epoch)
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **out)
+    os.replace(tmp, path)
   if max_to_keep is not None and max_to_keep >= 0:
     for _, p in list_checkpoints(path_ckpt)[:-max_to_keep or None]:
       if p != path:
-        os.remove(p)
+        _remove_checkpoint(p)
   return path
 
 
 def read_checkpoint(path: str) -> Dict[str, np.ndarray]:
-  with np.load(path) as z:
-    return {k: z[k] for k in z.files}
+  """`.npz` file or TensorFlow bundle prefix (`.../ckpt-7`) -> name -> array, srf_b200 names."""
+  if path.endswith(".npz"):
+    with np.load(path) as z:
+      return {k: z[k] for k in z.files}
+  from . import tf_bundle
+  if path.endswith(".index"):
+    path = path[:-len(".index")]
+  state, _ = tf_bundle.read_reference_checkpoint(path)
+  if not state:
+    raise ValueError("%s holds no variable of a SequenceRouter model" % path)
+  return state
 
 
 def load_checkpoint(model, path_ckpt: str, path_ckpt_epoch: Optional[int] = None, logger=None,
@@ -181,14 +216,14 @@ def load_checkpoint(model, path_ckpt: str, path_ckpt_epoch: Optional[int] = None
   `model`; returns the epoch offset (0 and nothing loaded when there is no checkpoint)."""
   loaded = None
   if path_ckpt_epoch is not None and path_ckpt_epoch > 0:
-    loaded = _ckpt_path(path_ckpt, path_ckpt_epoch)
-    if not os.path.exists(loaded):
-      raise FileNotFoundError(loaded)
+    loaded = dict(list_checkpoints(path_ckpt)).get(int(path_ckpt_epoch))
+    if loaded is None:
+      raise FileNotFoundError(os.path.join(path_ckpt, "ckpt-%d" % path_ckpt_epoch))
   else:
     loaded = latest_checkpoint(path_ckpt)
   epoch_offset = 0
   if loaded is not None:
-    epoch_offset = int(re.search(r"ckpt-(\d+)\.npz$", loaded).group(1))
+    epoch_offset = int(re.search(r"ckpt-(\d+)(\.npz)?$", loaded).group(1))
     load_state_dict(model, read_checkpoint(loaded), strict=strict)
   if logger is not None:
     logger.info("Loaded ckpt: %s", loaded)
@@ -224,12 +259,12 @@ def average_states(states: Sequence[Dict[str, np.ndarray]]) -> Dict[str, np.ndar
   return out
 
 
-def average_checkpoints(path_ckpt: str, model_average_num: int, logger=None) -> str:
+def average_checkpoints(path_ckpt: str, model_average_num: int, logger=None, fmt: str = "npz") -> str:
   """average_ckpt_sr.py:100-179: mean of the last `model_average_num` checkpoints, saved as the
   only checkpoint of `<path_ckpt>/avg` (that directory is recreated)."""
   ckpts = list_checkpoints(path_ckpt)[-model_average_num:]
   if not ckpts:
-    raise FileNotFoundError("no ckpt-*.npz under %s" % path_ckpt)
+    raise FileNotFoundError("no ckpt-* checkpoint under %s" % path_ckpt)
   for _, p in ckpts:
     if logger is not None:
       logger.info(p)
@@ -239,7 +274,7 @@ def average_checkpoints(path_ckpt: str, model_average_num: int, logger=None) -> 
   avg_dir = os.path.join(path_ckpt, "avg")
   if os.path.exists(avg_dir):
     shutil.rmtree(avg_dir)
-  out = save_checkpoint(avg, avg_dir, 1, max_to_keep=1)
+  out = save_checkpoint(avg, avg_dir, 1, max_to_keep=1, fmt=fmt)
   if logger is not None:
     logger.info("Saved to %s", out)
   return out

@@ -399,7 +399,7 @@ static int validate_layer(srf_handle* h, const srf_layer_desc* L, bool fwd = tru
   if (fwd && L->head_gamma && !L->out_logits)
     return fail(h, -1, "head requested but out_logits is NULL");
   if (L->uhat_mode != SRF_UHAT_FP32 && L->uhat_mode != SRF_UHAT_TF32 &&
-      L->uhat_mode != SRF_UHAT_BF16 && L->uhat_mode != SRF_UHAT_FP32X3)
+      L->uhat_mode != SRF_UHAT_BF16 && L->uhat_mode != SRF_UHAT_FP32X3 && L->uhat_mode != SRF_UHAT_F16)
     return fail(h, -4, "unknown uhat_mode %d", L->uhat_mode);
   if (L->O > 128) return fail(h, -3, "O = %d output capsules > 128 is not supported", L->O);
   if (L->D > 32 || L->d > 32)
@@ -480,9 +480,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int uhat_geometry(srf_handle* h, const srf_layer_desc* L, UhatGeom* g) {
+  // SRF_UHAT_F16 shapes the fused kernel does not take run here as TF32 (the same significand width)
   if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_BF16 &&
-      L->uhat_mode != SRF_UHAT_FP32X3)
-    return fail(h, -4, "tensor-core u_hat needs uhat_mode TF32, BF16 or FP32X3");
+      L->uhat_mode != SRF_UHAT_FP32X3 && L->uhat_mode != SRF_UHAT_F16)
+    return fail(h, -4, "tensor-core u_hat needs uhat_mode TF32, F16, BF16 or FP32X3");
   if (L->d % 4 != 0)
     return fail(h, -3, "tensor-core u_hat needs d %% 4 == 0 (got d=%d); use SRF_UHAT_FP32", L->d);
   if ((reinterpret_cast<uintptr_t>(L->emb) & 15) != 0)
@@ -696,7 +697,8 @@ enum { FUSED_FALLBACK = 1 << 20 };
 
 static bool fused_geometry(const srf_handle* h, const srf_layer_desc* L, FusedGeom* g) {
   if (h->no_fused) return false;
-  if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_FP32X3) return false;
+  if (L->uhat_mode != SRF_UHAT_TF32 && L->uhat_mode != SRF_UHAT_FP32X3 && L->uhat_mode != SRF_UHAT_F16)
+    return false;
   if (L->d % 4 != 0 || L->d > 32 || L->D > 20 || L->O > 64 || L->iters > 64) return false;
   if (L->emb && (reinterpret_cast<uintptr_t>(L->emb) & 15) != 0) return false;
   const int t4 = (L->D + 3) / 4;
@@ -704,7 +706,9 @@ static bool fused_geometry(const srf_handle* h, const srf_layer_desc* L, FusedGe
   g->opl = (L->O + 31) / 32;
   if (!srf::route_fused_supported(g->T4, g->opl)) return false;
   g->KX = L->d / 4;
-  g->KC = 2 * ((L->d + 1 + 7) / 8);
+  // 16-byte K chunks per operand row, incl. the bias column, a whole number of MMA K steps (2 chunks):
+  // 4 fp32 / tf32 elements per chunk, 8 fp16 elements
+  g->KC = L->uhat_mode == SRF_UHAT_F16 ? 2 * ((L->d + 1 + 15) / 16) : 2 * ((L->d + 1 + 7) / 8);
   g->I = (L->lpad + L->rpad + 1) * L->H;
   return true;
 }
@@ -717,7 +721,7 @@ static int get_packed_fused(srf_handle* h, const srf_layer_desc* L, const FusedG
       hit = &pw;
       break;
     }
-  const size_t nW = (size_t)g.I * parts * g.opl * T4 * g.KC * 512;
+  const size_t nW = (size_t)g.I * (parts ? parts : 1) * g.opl * T4 * g.KC * 512;   // parts 0 = FP16 image
   const size_t bytes = nW * sizeof(float);
   const bool same = hit && hit->I == g.I && hit->O == L->O && hit->D == L->D && hit->d == L->d;
   if (same && L->weights_version != 0 && hit->version == L->weights_version) {
@@ -771,7 +775,11 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   if (rc) return rc;
   const srf_layer_desc& L0 = layers[0];
   const int B = L0.B, S = L0.S, sdr = L0.sdr ? 1 : 0;
-  const int parts = L0.uhat_mode == SRF_UHAT_FP32X3 ? 2 : 1;
+  // operand images per W tile: 1 = TF32, 2 = hi + lo (3 x TF32), 0 = one FP16 image; kmode = the
+  // kernel's MODE template argument
+  const int parts = L0.uhat_mode == SRF_UHAT_FP32X3 ? 2 : (L0.uhat_mode == SRF_UHAT_F16 ? 0 : 1);
+  const int nimg = parts ? parts : 1;
+  const int kmode = parts == 2 ? 1 : (parts == 0 ? 2 : 0);
   std::vector<FusedGeom> geo(n);
   int T4 = 0, OPLM = 0, KCmax = 0;
   for (int l = 0; l < n; ++l) {
@@ -912,7 +920,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
     bool same = (int)h->fz_arena_keys.size() == n;
     for (int l = 0; l < n; ++l) {
       arena_off[l] = arena_total;
-      arena_total += (((size_t)geo[l].I * parts * geo[l].opl * T4 * geo[l].KC * 512 * sizeof(float)) + 255) & ~(size_t)255;
+      arena_total += (((size_t)geo[l].I * nimg * geo[l].opl * T4 * geo[l].KC * 512 * sizeof(float)) + 255) & ~(size_t)255;
       if (same) {
         const PackedWeights& k = h->fz_arena_keys[l];
         const srf_layer_desc& L = layers[l];
@@ -1071,21 +1079,22 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   // W ring: a stage is G consecutive tiles fetched by ONE bulk copy (the copy rate is set by the
   // bytes issued per barrier round trip: single 12 KB copies reach 19 B/clk/SM, 48 KB copies 70,
   // profiles/r2_ubench.txt); at least 3 stages, G as large as fits up to ~48 KB
-  const size_t wpair = (size_t)KCmax * 2048 * parts;
+  const size_t wpair = (size_t)KCmax * 2048 * nimg;
   int G = (int)(49152 / wpair);
   if (G < 1) G = 1;
   int nwst = 0;
   for (; G >= 1; --G) {
     nwst = 8;
-    while (nwst > 3 && srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst, G * wpair) > (size_t)h->max_smem) --nwst;
-    if (srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst, G * wpair) <= (size_t)h->max_smem) break;
+    while (nwst > 3 && srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst, G * wpair) > (size_t)h->max_smem) --nwst;
+    if (srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst, G * wpair) <= (size_t)h->max_smem) break;
   }
   // the MMA issuers address a capsule's tiles through at most three ring stages
   if (G < 1 || T4 * OPLM >= 2 * G + 2) return FUSED_FALLBACK;   // the two-kernel path takes this shape
-  const size_t smem = srf::route_fused_smem_bytes(OPLM, KCmax, parts == 2, nwst, G * wpair);
+  const size_t smem = srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst, G * wpair);
   p.gtiles = G;
   p.wstage_bytes = (int)(G * wpair);
   p.xtile_bytes = KCmax * 32 * 16;
+  p.xstg_bytes = 2 * KCmax * 32 * 16;
   p.nwst = nwst;
   p.dbg = h->dbg;
   p.n_layers = n;
@@ -1110,7 +1119,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
     const void* win = n > 1 && h->l2_persist_max > 0 && getenv("SRF_L2_WINDOW") ? h->fz_arena : nullptr;
     size_t win_bytes = win ? (arena_total < h->l2_window_max ? arena_total : h->l2_window_max) : 0;
     const float hit = win_bytes > h->l2_persist_max ? (float)h->l2_persist_max / (float)win_bytes : 1.0f;
-    e = srf::launch_route_fused(p, T4, OPLM, parts == 2, grid, smem, stream, win, win_bytes, hit);
+    e = srf::launch_route_fused(p, T4, OPLM, kmode, grid, smem, stream, win, win_bytes, hit);
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -1121,7 +1130,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   snprintf(nm, sizeof(nm),
            "route_fused_kernel<T4=%d,OPL=%d,%s> %s layers=%d grid=%d groups=%d rounds=%d maxC=%d wstages=%dx%d "
            "tiles smem=%zu",
-           T4, OPLM, parts == 2 ? "3xTF32" : "tf32", sdr ? "SDR-wavefront" : "DR", n, grid, ngroups, rounds,
+           T4, OPLM, parts == 2 ? "3xTF32" : (parts == 0 ? "f16" : "tf32"), sdr ? "SDR-wavefront" : "DR", n, grid, ngroups, rounds,
            maxC, nwst, G, smem);
   h->last_kernel = nm;
   return 0;

@@ -37,6 +37,7 @@
 // launch drains and the host reports an error instead of hanging the GPU.
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -87,13 +88,48 @@ __global__ void pack_weights_fused_kernel(const float* __restrict__ W, const flo
   }
 }
 
+// FP16 operand images (SRF_UHAT_F16): Wf half[i][m][c][r][8], chunk c holds l = 8c .. 8c+7, values
+// rounded to nearest-even fp16 (the same 11-bit significand as TF32) and clamped to the finite range
+__global__ void pack_weights_fused_f16_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                              __half* __restrict__ Wf, int I, int O, int D, int d, int T4,
+                                              int OPL, int KC) {
+  const int NT = OPL * T4;
+  const long long n = (long long)I * NT * KC * 1024;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const int li = (int)(e & 7);
+    long long t = e >> 3;
+    const int r = (int)(t & 127);
+    t >>= 7;
+    const int c = (int)(t % KC);
+    t /= KC;
+    const int m = (int)(t % NT);
+    const int i = (int)(t / NT);
+    const int jb = m / T4, k4 = m - jb * T4;
+    const int j = jb * 32 + (r & 31), k = 4 * k4 + (r >> 5), l = 8 * c + li;
+    float v = 0.f;
+    if (j < O && k < D) {
+      if (l < d)
+        v = W[(((long long)i * O + j) * D + k) * d + l];
+      else if (l == d)
+        v = bias[((long long)i * O + j) * D + k];
+    }
+    Wf[e] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  }
+}
+
+// parts: 1 = TF32 image, 2 = hi + lo images (3 x TF32), 0 = FP16 image
 void launch_pack_weights_fused(const float* W, const float* bias, float* Wf, int I, int O, int D, int d,
                                int T4, int OPL, int KC, int parts, cudaStream_t stream) {
-  const long long n = (long long)I * parts * OPL * T4 * KC * 512;
+  const long long n = (long long)I * (parts ? parts : 1) * OPL * T4 * KC * 512;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  pack_weights_fused_kernel<<<blocks, 256, 0, stream>>>(W, bias, Wf, I, O, D, d, T4, OPL, KC, parts);
+  if (parts == 0)
+    pack_weights_fused_f16_kernel<<<blocks, 256, 0, stream>>>(W, bias, reinterpret_cast<__half*>(Wf), I, O, D, d,
+                                                              T4, OPL, KC);
+  else
+    pack_weights_fused_kernel<<<blocks, 256, 0, stream>>>(W, bias, Wf, I, O, D, d, T4, OPL, KC, parts);
 }
 
 namespace {
@@ -103,6 +139,7 @@ constexpr int FZ_TF = 16;                // frames per team
 constexpr int FZ_MATH_WARPS = 8;
 constexpr int FZ_THREADS = 384;          // 4 service warps + 8 math warps
 constexpr int FZ_CAP_RING = 8;           // capsule-completion barriers (>= x ring depth and TMEM buffers)
+constexpr int FZ_STG = 4;                // fp32 staging slots of the FP16-image x loader (3 capsules of lookahead)
 constexpr int FZ_XST_MAX = 8;            // x-tile ring depth (tf32; the 3 x TF32 build keeps two images: 4)
 constexpr long long FZ_TIMEOUT = 6000000000ll;  // ~3 s of SM clocks
 
@@ -227,9 +264,30 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32
       "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], TF32; descriptors given as (low word, shared high word)
+// D[tmem] (+)= A[smem] * B[smem], TF32 (or FP16 operands: kind::f16); descriptors given as (low word,
+// shared high word)
+template <bool F16>
 __device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                             uint32_t idesc, bool accumulate) {
+  if (F16) {
+    if (accumulate)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "setp.ne.b32 p, 1, 0;\n\t"
+          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+          : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "setp.ne.b32 p, 0, 0;\n\t"
+          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+          : "memory");
+    return;
+  }
   if (accumulate)
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
@@ -249,7 +307,7 @@ __device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint
 }
 // all MMAs of one capsule: NTA tiles x NKS K steps (x 3 in the 3 x TF32 build), no run-time
 // predicates between the instructions
-template <int NTA, int NKS, bool X3>
+template <int NTA, int NKS, bool X3, bool F16>
 __device__ __forceinline__ void mma_issue_capsule(uint32_t d_base, const uint32_t (&a_lo)[NTA], uint32_t b_lo,
                                                   uint32_t blo_lo, uint32_t wtile16, uint32_t desc_hi,
                                                   uint32_t idesc) {
@@ -257,10 +315,10 @@ __device__ __forceinline__ void mma_issue_capsule(uint32_t d_base, const uint32_
   for (int m = 0; m < NTA; ++m) {
 #pragma unroll
     for (int ks = 0; ks < NKS; ++ks) {
-      mma_tf32_lo(d_base + m * FZ_N, a_lo[m] + ks * 256, b_lo + ks * (2 * FZ_N), desc_hi, idesc, ks > 0);
+      mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo[m] + ks * 256, b_lo + ks * (2 * FZ_N), desc_hi, idesc, ks > 0);
       if (X3) {
-        mma_tf32_lo(d_base + m * FZ_N, a_lo[m] + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), desc_hi, idesc, true);
-        mma_tf32_lo(d_base + m * FZ_N, a_lo[m] + ks * 256, blo_lo + ks * (2 * FZ_N), desc_hi, idesc, true);
+        mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo[m] + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), desc_hi, idesc, true);
+        mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo[m] + ks * 256, blo_lo + ks * (2 * FZ_N), desc_hi, idesc, true);
       }
     }
   }
@@ -516,8 +574,10 @@ __device__ __forceinline__ void fz_step_b(float (&ta)[OPL][T4][FZ_TF], uint32_t 
 
 // T4 = ceil(D/4) tiles per block of 32 output capsules, OPL = blocks of 32 output capsules the
 // build holds (a layer may use fewer: FusedLayer::opl), X3 = 3 x TF32 split
-template <int T4, int OPL, bool X3>
+template <int T4, int OPL, int MODE>
 __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedParams p) {
+  constexpr bool X3 = MODE == 1;      // 3 x TF32 split
+  constexpr bool F16 = MODE == 2;     // FP16 operand images (8 elements per 16-byte chunk, K = 16 per MMA)
   constexpr int NT = T4 * OPL;        // M tiles per input capsule (at most)
   constexpr int T = 4 * T4;           // padded output capsule dim
   constexpr int OP = 32 * OPL;        // padded output capsules
@@ -557,7 +617,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
   uint8_t* sW = smem_raw;                                     // [NWST][wstage]
   uint8_t* sX = sW + (size_t)NWST * wstage;                   // [XST][xtile]  (x, or x_hi)
   uint8_t* sXlo = sX + (size_t)XST * p.xtile_bytes;        // [XST][xtile]  (X3)
-  float* sP = reinterpret_cast<float*>(sXlo + (X3 ? (size_t)XST * p.xtile_bytes : 0));  // [2][2 teams][4][OPL][32][16]
+  // FP16 images: fp32 staging ring of the x loader [FZ_STG][4-float chunk][frame][16 B]
+  uint8_t* sStg = sXlo + (X3 ? (size_t)XST * p.xtile_bytes : 0);
+  float* sP = reinterpret_cast<float*>(sStg + (F16 ? (size_t)FZ_STG * p.xstg_bytes : 0));  // [2][2 teams][4][OPL][32][16]
   float* sC = sP + 2 * 2 * 4 * OPL * 32 * 16;                 // [2][2 teams][OPL][32][16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * 2 * OPL * 32 * 16);
   const uint32_t w_full = ptx::smem_u32(bars);               // [NWST]   (8 bytes each)
@@ -586,11 +648,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
   }
   // constant part of the x tiles: chunk KX carries the 1 that multiplies the bias column of W
   // (x_hi image), everything above the TMA box is zero; the TMA never writes these chunks
-  for (int e = tid; e < XST * (KC - KX) * FZ_N; e += FZ_THREADS) {
-    const int st = e / ((KC - KX) * FZ_N), rem = e - st * ((KC - KX) * FZ_N);
-    const int c = KX + rem / FZ_N, f = rem % FZ_N;
+  // (FP16 images: the loader writes the chunks up to and including the one that holds the 1; the
+  // chunks above it are zero)
+  const int KXW = F16 ? (4 * KX + 1 + 7) / 8 : KX;   // chunks the x loader (re)writes per tile
+  for (int e = tid; e < XST * (KC - KXW) * FZ_N; e += FZ_THREADS) {
+    const int st = e / ((KC - KXW) * FZ_N), rem = e - st * ((KC - KXW) * FZ_N);
+    const int c = KXW + rem / FZ_N, f = rem % FZ_N;
     float4* dst = reinterpret_cast<float4*>(sX + (size_t)st * xtile + ((size_t)c * FZ_N + f) * 16);
-    *dst = make_float4(c == KX ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    *dst = make_float4((!F16 && c == KX) ? 1.f : 0.f, 0.f, 0.f, 0.f);
     if (X3) *reinterpret_cast<float4*>(sXlo + (size_t)st * xtile + ((size_t)c * FZ_N + f) * 16) =
         make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -624,7 +689,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
     // thread's own MMAs on the stage have retired (at once if it had none).
     if (lane == 0) {
       const int me = swarp;
-      const uint32_t idesc = ptx::make_idesc_tf32(128, FZ_N);
+      const uint32_t idesc = F16 ? ptx::make_idesc_f16(128, FZ_N) : ptx::make_idesc_tf32(128, FZ_N);
       // K-major no-swizzle descriptors: low word = start address >> 4 | LBO >> 4 << 16, high word =
       // SBO >> 4 | version 1; only the 14-bit address field changes from MMA to MMA
       constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
@@ -638,9 +703,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
       // event trace of the first 512 capsules of CTA 0 and CTA 80: 32-bit clock per event
       unsigned* trace = nullptr;
       if (p.dbg && me == 0 && (blockIdx.x == 0 || blockIdx.x == 80))
-        trace = reinterpret_cast<unsigned*>(p.dbg) + 6000 + (blockIdx.x == 0 ? 0 : 2560);
+        trace = reinterpret_cast<unsigned*>(p.dbg) + 6000 + (blockIdx.x == 0 ? 0 : 3072);
       unsigned ncap_tr = 0;
-#define FZ_MK(slot) if (trace && ncap_tr < 512) trace[ncap_tr * 5 + (slot)] = (unsigned)clock();
+#define FZ_MK(slot) if (trace && ncap_tr < 512) trace[ncap_tr * 6 + (slot)] = (unsigned)clock();
 #else
 #define FZ_MK(slot)
 #endif
@@ -677,6 +742,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
                   w_seen = g + 1;
                 }
               }
+              FZ_MK(5)
               ptx::tc_fence_after();
               const uint32_t d_base = tmem_base + (uint32_t)(buf * TCOLS);
               const uint32_t b_lo = b_lo0 + (uint32_t)xs * xtile16, blo_lo = blo_lo0 + (uint32_t)xs * xtile16;
@@ -685,16 +751,17 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               const uint32_t base1 = a_lo0 + ((gs + 1) % NWST) * wstage16 + (uint32_t)(tin - G) * wpair16;
               const uint32_t base2 = a_lo0 + ((gs + 2) % NWST) * wstage16 + (uint32_t)(tin - 2 * G) * wpair16;
 #ifndef SRF_FUSED_NOMMA
-              if (nt == NT && (nks == 2 || nks == 3 || nks == 5)) {
+              if (nt == NT && (nks == 2 || nks == 3 || nks == 5 || (F16 && nks == 1))) {
                 uint32_t al[NT];
 #pragma unroll
                 for (int m = 0; m < NT; ++m) {
                   const int t = tin + m;
                   al[m] = (t < G ? base0 : (t < 2 * G ? base1 : base2)) + (uint32_t)m * wpair16;
                 }
-                if (nks == 3) mma_issue_capsule<NT, 3, X3>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
-                else if (nks == 2) mma_issue_capsule<NT, 2, X3>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
-                else mma_issue_capsule<NT, 5, X3>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                if (nks == 3) mma_issue_capsule<NT, 3, X3, F16>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else if (nks == 2) mma_issue_capsule<NT, 2, X3, F16>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else if (F16 && nks == 1) mma_issue_capsule<NT, 1, false, true>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else mma_issue_capsule<NT, 5, X3, F16>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
               } else {
 #pragma unroll
                 for (int m = 0; m < NT; ++m) {
@@ -704,10 +771,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
 #pragma unroll
                     for (int ks = 0; ks < 5; ++ks) {
                       if (ks < nks) {
-                        mma_tf32_lo(d_base + m * FZ_N, a_lo + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, ks > 0);
+                        mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, ks > 0);
                         if (X3) {
-                          mma_tf32_lo(d_base + m * FZ_N, a_lo + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
-                          mma_tf32_lo(d_base + m * FZ_N, a_lo + ks * 256, blo_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                          mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                          mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo + ks * 256, blo_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
                         }
                       }
                     }
@@ -787,12 +854,35 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
           if (need > p.S) need = p.S;
           wt.counter(prog, need, 101);
         }
+        // FP16 images: the frame's fp32 capsule is staged by cp.async FZ_STG - 1 capsules ahead of its
+        // conversion (the x of a step is complete once the progress wait above has passed)
+        const int ncapP = item.i_hi - item.i_lo, qtotal = iters * ncapP;
+        const uint32_t stg_a = ptx::smem_u32(sStg) + (uint32_t)lane * 16u;
+        auto stage_x = [&](int q) {
+          if (q < qtotal) {
+            const int iq = item.i_lo + q % ncapP;
+            const int wq = iq / H, hq = iq - wq * H;
+            const int sq = s0 - lpad + wq;
+            const bool okq = frame_ok && sq >= 0 && sq < p.S;
+            const float* srcq = base + ((size_t)(okq ? sq : 0) * H + hq) * d;
+            const uint32_t dq = stg_a + (uint32_t)(q % FZ_STG) * (uint32_t)p.xstg_bytes;
+            const uint32_t nb = okq ? 16u : 0u;
+            for (int c = 0; c < KX; ++c)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq + (uint32_t)c * (FZ_N * 16u)),
+                           "l"(srcq + 4 * c), "r"(nb)
+                           : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int q = 0;
+        if (F16)
+          for (int qq = 0; qq < FZ_STG - 1; ++qq) stage_x(qq);
         for (int pass = 0; pass < iters; ++pass) {
           int i = item.i_lo;
           for (int t0 = 0; t0 < ntiles; t0 += G) {
           const int cnt = ntiles - t0 < G ? ntiles - t0 : G;
           const int i_end = item.i_lo + (t0 + cnt - 1) / nt + 1;   // capsules with a tile in this stage
-          for (; i < i_end; ++i, ++n_x) {
+          for (; i < i_end; ++i, ++n_x, ++q) {
             const int w = i / H, h = i - w * H;
             const int s = s0 - lpad + w;
             const bool ok = frame_ok && s >= 0 && s < p.S;
@@ -804,7 +894,41 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               wt.mbar(cap_done + 8u * (prev % FZ_CAP_RING), (prev / FZ_CAP_RING) & 1, 102);
             }
             const uint32_t dst = ptx::smem_u32(sX) + (uint32_t)xs * xtile + (uint32_t)lane * 16u;
-            if (!X3) {
+            if (F16) {
+              // staged fp32 -> fp16 (rn; clamped to the finite fp16 range): chunk c holds the elements
+              // 8c .. 8c+7, element d is the 1 that multiplies the bias column of W
+              stage_x(q + FZ_STG - 1);
+              asm volatile("cp.async.wait_group %0;" ::"n"(FZ_STG - 1) : "memory");
+              const uint32_t sq_a = stg_a + (uint32_t)(q % FZ_STG) * (uint32_t)p.xstg_bytes;
+              for (int c0 = 0; c0 < KXW; c0 += 2) {
+                float4 v[4];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const int qi = 2 * c0 + q4;
+                  v[q4] = make_float4(qi == KX ? 1.f : 0.f, 0.f, 0.f, 0.f);
+                  if (qi < KX) v[q4] = lds128f(sq_a + (uint32_t)qi * (FZ_N * 16u));
+                }
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                  if (c0 + cc < KXW) {
+                    uint32_t h[4];
+                    const float4 a = v[2 * cc], b2 = v[2 * cc + 1];
+                    const float e[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                      const float lo = fminf(fmaxf(e[2 * q4], -65504.f), 65504.f);
+                      const float hi = fminf(fmaxf(e[2 * q4 + 1], -65504.f), 65504.f);
+                      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[q4]) : "f"(hi), "f"(lo));
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(c0 + cc) * (FZ_N * 16u)),
+                                 "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                                 : "memory");
+                  }
+                }
+              }
+              ptx::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's reads
+              mbar_arrive_a(x_full + 8u * xs);
+            } else if (!X3) {
               const uint32_t nbytes = ok ? 16u : 0u;
               for (int c = 0; c < KX; ++c)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)c * (FZ_N * 16u)),
@@ -1276,17 +1400,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
 
 // ---------------------------------------------------------------------------------------
 size_t route_fused_smem_bytes(int OPL, int KC, int x3, int nwst, size_t wstage_bytes) {
+  // mode 2 (FP16 images) has one image like tf32 plus the loader's fp32 staging ring: KC chunks of 8
+  // halfs hold at most 2 * KC chunks of 4 floats
+  const size_t stg = x3 == 2 ? (size_t)FZ_STG * (2 * (size_t)KC) * FZ_N * 16 : 0;
+  x3 = x3 == 1;
   const size_t xt = (size_t)KC * FZ_N * 16;
   const size_t XST = x3 ? FZ_XST_MAX / 2 : FZ_XST_MAX;
-  return 1024 + (size_t)nwst * wstage_bytes + XST * xt * (x3 ? 2 : 1) +
+  return 1024 + stg + (size_t)nwst * wstage_bytes + XST * xt * (x3 ? 2 : 1) +
          sizeof(float) * 2 * (2 * 4 * OPL * 32 * 16 + 2 * OPL * 32 * 16) +
          sizeof(uint64_t) * (2 * (size_t)nwst + 2 * XST + 16) + 64;
 }
 
-template <int T4, int OPL, bool X3>
+template <int T4, int OPL, int MODE>
 static cudaError_t launch_fused_variant(const FusedParams& p, int grid, size_t smem, cudaStream_t stream,
                                         const void* l2_window, size_t l2_window_bytes, float l2_hit_ratio) {
-  auto kern = route_fused_kernel<T4, OPL, X3>;
+  auto kern = route_fused_kernel<T4, OPL, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -1320,8 +1448,9 @@ cudaError_t launch_route_fused(const FusedParams& p, int T4, int OPL, int x3, in
                                float l2_hit_ratio) {
 #define SRF_FUSED(T4_, OPL_)                                                              \
   if (T4 == T4_ && OPL == OPL_)                                                           \
-    return x3 ? launch_fused_variant<T4_, OPL_, true>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio) \
-              : launch_fused_variant<T4_, OPL_, false>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio);
+    return x3 == 1 ? launch_fused_variant<T4_, OPL_, 1>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio) \
+         : x3 == 2 ? launch_fused_variant<T4_, OPL_, 2>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio) \
+                   : launch_fused_variant<T4_, OPL_, 0>(p, grid, smem, stream, l2_window, l2_window_bytes, l2_hit_ratio);
   SRF_FUSED(2, 1)
   SRF_FUSED(2, 2)
   SRF_FUSED(4, 1)

@@ -208,6 +208,7 @@ struct FusedParams {
   int gtiles;                 // W tiles (hi + lo images) per ring stage = one bulk copy
   int wstage_bytes;           // ring stage stride
   int xtile_bytes;            // x ring stage stride (widest layer)
+  int xstg_bytes;             // FP16 images: stride of the x loader's fp32 staging slots
   unsigned long long* dbg;    // optional phase timers [CTA][16] (clock64 sums), null = off
   // The geometry of every CTA's work, as kernel parameters: the MMA issuers derive their smem
   // descriptors from it, and only values that are provably warp-uniform (parameters, blockIdx)

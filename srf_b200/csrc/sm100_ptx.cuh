@@ -149,6 +149,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// instruction descriptor for kind::f16 with FP16 A and B (format 0), fp32 accumulate, K-major, M=128
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 }  // namespace ptx
 }  // namespace srf

@@ -47,11 +47,11 @@ for i, n in names.items():
 print('sum %.0f clk per pass' % tot)
 
 tr = buf.reshape(-1).view(np.uint32)
-for name, off in (('CTA 0', 6000), ('CTA 80', 6000 + 2560)):
-  e = tr[off:off + 2560].reshape(512, 5).astype(np.int64)
+for name, off in (('CTA 0', 6000), ('CTA 80', 6000 + 3072)):
+  e = tr[off:off + 3072].reshape(512, 6).astype(np.int64)
   e = e[40:500]   # steady state
   d = lambda a, b: ((e[:, b] - e[:, a]) & 0xffffffff)
   nxt = ((e[1:, 0] - e[:-1, 4]) & 0xffffffff)
-  print('MMA issuer trace %s (clk per capsule, median / mean): wait x_full %d / %d; wait t_empty(tile 0) %d / %d; issue MMAs (incl. per-tile waits) %d / %d; commits %d / %d; loop back %d / %d' % (
-      name, np.median(d(0, 1)), d(0, 1).mean(), np.median(d(1, 2)), d(1, 2).mean(), np.median(d(2, 3)), d(2, 3).mean(),
+  print('MMA issuer trace %s (clk per capsule, median / mean): wait x_full %d / %d; wait t_empty(tile 0) %d / %d; wait w_full %d / %d; issue MMAs %d / %d; commits %d / %d; loop back %d / %d' % (
+      name, np.median(d(0, 1)), d(0, 1).mean(), np.median(d(1, 2)), d(1, 2).mean(), np.median(d(2, 5)), d(2, 5).mean(), np.median(d(5, 3)), d(5, 3).mean(),
       np.median(d(3, 4)), d(3, 4).mean(), np.median(nxt), nxt.mean()))

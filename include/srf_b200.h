@@ -158,6 +158,18 @@ int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* layer, const srf_la
                         void* stream);
 
 /*
+ * Backward of the whole routing stack (tape.gradient through `for i in range(self.enc_num)`,
+ * tfsr/trainer_sr.py:62-71): srf_route_layer_bwd for n = n_layers-1 ... 0.  `layers` are the
+ * descriptors of the training forward (srf_route_stack_fwd with out_caps AND out_raw given for every
+ * layer, or one srf_route_layer_fwd per layer): a NULL layers[n].emb (n > 0) means layers[n-1].out_caps,
+ * the saved input of layer n.  grads[n].v_raw is layers[n].out_raw of that forward; grads[last].d_logits
+ * is dL/dlogits; for n < last a NULL grads[n].d_out means grads[n+1].d_emb (which must then be given, as
+ * must every d_emb but grads[0]'s).  All gradient outputs accumulate: zero them first.
+ */
+int srf_route_stack_bwd(srf_handle* h, const srf_layer_desc* layers, const srf_layer_grads* grads,
+                        int32_t n_layers, void* stream);
+
+/*
  * Greedy CTC decode (the parity criterion of SURVEY.md 8c; blank = class_n - 1,
  * tfsr/trainer_sr.py:133-134): argmax per routing frame for s < lens[b], collapse repeats, drop
  * blank.  logits [B,S,C]; lens [B] int32 (routing frames); out_ids [B,S] int32 (first out_lens[b]

@@ -15,7 +15,7 @@ UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF1
 
 # every symbol include/srf_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ("srf_version", "srf_create", "srf_destroy", "srf_last_error", "srf_route_layer_fwd",
-           "srf_route_stack_fwd", "srf_route_layer_bwd", "srf_ctc_greedy_decode", "srf_ctc_loss",
+           "srf_route_stack_fwd", "srf_route_layer_bwd", "srf_route_stack_bwd", "srf_ctc_greedy_decode", "srf_ctc_loss",
            "srf_adam_step", "srf_uhat_fwd", "srf_capsulate_fwd", "srf_profile_begin", "srf_profile_end", "srf_launch_count",
            "srf_last_kernel")
 
@@ -83,6 +83,8 @@ def load() -> ctypes.CDLL:
   lib.srf_route_stack_fwd.restype = c_int
   lib.srf_route_layer_bwd.argtypes = [c_void_p, POINTER(LayerDesc), POINTER(LayerGrads), c_void_p]
   lib.srf_route_layer_bwd.restype = c_int
+  lib.srf_route_stack_bwd.argtypes = [c_void_p, POINTER(LayerDesc), POINTER(LayerGrads), c_int32, c_void_p]
+  lib.srf_route_stack_bwd.restype = c_int
   lib.srf_ctc_greedy_decode.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                         c_void_p, c_void_p, c_void_p]
   lib.srf_ctc_greedy_decode.restype = c_int

@@ -165,6 +165,10 @@ extern "C" int srf_create(int device, srf_handle** out) {
   if (const char* s = getenv("SRF_FORCE_FUSED")) h->force_fused = atoi(s);
   h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  // the persisting carve-out takes its share of L2 away from ALL normal traffic of the device (measured:
+  // the two-kernel fp32x3 path fell from 42 to 65 ms per cfg-3 step with it set), so it is reserved
+  // only when the experiment that uses it is switched on
+  if (!getenv("SRF_L2_WINDOW")) h->l2_persist_max = 0;
   if (h->l2_persist_max > 0) {
     DeviceGuard g(device);
     if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
@@ -1538,3 +1542,31 @@ extern "C" int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, 
   }
   return 0;
 }
+
+// the whole routing stack, backward: srf_route_layer_bwd from the last layer down, the gradient
+// w.r.t. a layer's input feeding the next call (reference: tape.gradient through the stack,
+// tfsr/trainer_sr.py:62-71)
+extern "C" int srf_route_stack_bwd(srf_handle* h, const srf_layer_desc* layers, const srf_layer_grads* grads,
+                                   int32_t n_layers, void* stream) {
+  if (!h) return fail(nullptr, -1, "handle is NULL");
+  if (!layers || !grads || n_layers <= 0) return fail(h, -1, "layers / grads is NULL or n_layers <= 0");
+  for (int n = n_layers - 1; n >= 0; --n) {
+    srf_layer_desc L = layers[n];
+    srf_layer_grads G = grads[n];
+    if (!L.emb) {
+      if (n == 0) return fail(h, -1, "layers[0].emb is NULL");
+      L.emb = layers[n - 1].out_caps;
+      if (!L.emb) return fail(h, -1, "layer %d: the input (layers[%d].out_caps of the forward) is NULL", n, n - 1);
+    }
+    if (n < n_layers - 1) {
+      if (!G.d_out) G.d_out = grads[n + 1].d_emb;
+      if (!G.d_out) return fail(h, -1, "layer %d: grads[%d].d_emb is needed to continue the backward", n, n + 1);
+      G.d_logits = nullptr;
+    }
+    if (n > 0 && !G.d_emb) return fail(h, -1, "layer %d: d_emb is required for every layer but the first", n);
+    const int rc = srf_route_layer_bwd(h, &L, &G, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+

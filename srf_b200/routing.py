@@ -229,6 +229,75 @@ def route_stack_fwd(emb, layers: Sequence[LayerArgs], handle: Optional[Handle] =
   return out_logits
 
 
+def route_stack_fwd_train(emb, layers: Sequence[LayerArgs], handle: Optional[Handle] = None):
+  """Training forward of the whole stack in ONE library call (srf_route_stack_fwd with out_caps and
+  out_raw for every layer: the fused layer-wavefront kernel when the shape and mode allow it).
+  -> (logits, [layer outputs], [pre-LayerNorm capsules]) -- what srf_route_stack_bwd needs saved."""
+  emb = as_device_tensor(emb)
+  if emb.dim() != 4:
+    raise ValueError("emb must be [B,S,H,d], got %s" % (tuple(emb.shape),))
+  if not layers or layers[-1].head_gamma is None:
+    raise ValueError("the last layer must carry the head (head_gamma/head_beta)")
+  h = handle or default_handle(emb.device)
+  B, S, H, d = emb.shape
+  n = len(layers)
+  descs = (_lib.LayerDesc * n)()
+  caps, raws = [], []
+  logits = torch.empty((B, S, layers[-1].W.shape[1]), dtype=torch.float32, device=emb.device)
+  for i, a in enumerate(layers):
+    _prep(a, emb.device)
+    O, D = a.W.shape[1], a.W.shape[2]
+    caps.append(torch.empty((B, S, O, D), dtype=torch.float32, device=emb.device))
+    raws.append(torch.empty((B, S, O, D), dtype=torch.float32, device=emb.device))
+    _fill_desc(descs[i], a, emb if i == 0 else None, B, S, H, d, caps[i], logits if i == n - 1 else None)
+    descs[i].out_raw = _ptr(raws[i])
+    H, d = O, D
+  stream = ctypes.c_void_p(torch.cuda.current_stream(emb.device).cuda_stream)
+  rc = h.lib.srf_route_stack_fwd(h._h, descs, n, stream)
+  _lib.check(h.lib, h._h, rc, "srf_route_stack_fwd")
+  return logits, caps, raws
+
+
+def route_stack_bwd(emb, layers: Sequence[LayerArgs], caps, raws, d_logits, need_d_emb: bool = True,
+                    handle: Optional[Handle] = None):
+  """Backward of the whole stack in ONE library call (srf_route_stack_bwd).  `caps` / `raws` are what
+  route_stack_fwd_train (or the per-layer training forwards) returned.  -> list of per-layer gradient
+  dicts (keys as route_layer_bwd; "d_emb" of layer 0 is the gradient w.r.t. `emb`)."""
+  emb = as_device_tensor(emb)
+  h = handle or default_handle(emb.device)
+  dev = emb.device
+  B, S, H, d = emb.shape
+  n = len(layers)
+  descs = (_lib.LayerDesc * n)()
+  grs = (_lib.LayerGrads * n)()
+  z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+  out, keep = [], []
+  d_logits = as_device_tensor(d_logits, dev)
+  for i, a in enumerate(layers):
+    _prep(a, dev)
+    I, O, D, _ = a.W.shape
+    last = i == n - 1
+    _fill_desc(descs[i], a, emb if i == 0 else None, B, S, H, d, caps[i], None)
+    g = {"dW": z(I, O, D, d), "dbias": z(I, O, D),
+         "dgamma": z(O * D) if a.ln_gamma is not None else None,
+         "dbeta": z(O * D) if a.ln_gamma is not None else None,
+         "dhead_gamma": z(O) if last else None, "dhead_beta": z(O) if last else None,
+         "d_emb": z(B, S, H, d) if (need_d_emb or i > 0) else None}
+    d_raw = torch.empty((B, S, O, D), dtype=torch.float32, device=dev)
+    keep.append(d_raw)
+    gr = grs[i]
+    gr.v_raw, gr.d_raw = _ptr(as_device_tensor(raws[i], dev)), _ptr(d_raw)
+    gr.d_logits = _ptr(d_logits) if last else None
+    gr.dW, gr.dbias, gr.dgamma, gr.dbeta = _ptr(g["dW"]), _ptr(g["dbias"]), _ptr(g["dgamma"]), _ptr(g["dbeta"])
+    gr.dhead_gamma, gr.dhead_beta, gr.d_emb = _ptr(g["dhead_gamma"]), _ptr(g["dhead_beta"]), _ptr(g["d_emb"])
+    out.append(g)
+    H, d = O, D
+  stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  rc = h.lib.srf_route_stack_bwd(h._h, descs, grs, n, stream)
+  _lib.check(h.lib, h._h, rc, "srf_route_stack_bwd")
+  return out
+
+
 def uhat_fwd(emb, W, bias, lpad: int, rpad: int, uhat_mode: str = "tf32",
              handle: Optional[Handle] = None) -> torch.Tensor:
   """Prediction vectors alone (srf_uhat_fwd, naive:150-159): [B,S,H,d] -> [B,S,I,O,D] fp32,
@@ -271,9 +340,11 @@ def route_layer_fwd_train(emb, args: LayerArgs, handle: Optional[Handle] = None)
 
 
 def route_layer_bwd(emb, args: LayerArgs, v_raw, d_out=None, d_logits=None, need_d_emb=True,
-                    handle: Optional[Handle] = None):
+                    handle: Optional[Handle] = None, out: Optional[dict] = None):
   """Backward of one layer (srf_route_layer_bwd).  Returns a dict with dW, dbias, dgamma, dbeta,
-  dhead_gamma, dhead_beta (None where the layer has no such parameter) and d_emb."""
+  dhead_gamma, dhead_beta (None where the layer has no such parameter) and d_emb.  `out`: already
+  ZEROED float32 device tensors to accumulate into instead of fresh ones (any subset of the keys;
+  e.g. views into a flat gradient buffer)."""
   emb = as_device_tensor(emb)
   h = handle or default_handle(emb.device)
   _prep(args, emb.device)
@@ -286,7 +357,26 @@ def route_layer_bwd(emb, args: LayerArgs, v_raw, d_out=None, d_logits=None, need
        "dbeta": z(O * D) if args.ln_gamma is not None else None,
        "dhead_gamma": z(O) if d_logits is not None else None,
        "dhead_beta": z(O) if d_logits is not None else None,
-       "d_emb": z(B, S, H, d) if need_d_emb else None}
+       "d_emb": z(B, S, H, d) if need_d_emb else None} if out is None else None
+  if out is not None:
+    want = {"dW": ((I, O, D, d), True), "dbias": ((I, O, D), True),
+            "dgamma": ((O * D,), args.ln_gamma is not None), "dbeta": ((O * D,), args.ln_gamma is not None),
+            "dhead_gamma": ((O,), d_logits is not None), "dhead_beta": ((O,), d_logits is not None),
+            "d_emb": ((B, S, H, d), need_d_emb)}
+    g = {}
+    for k, (shape, needed) in want.items():
+      t = out.get(k)
+      if not needed:
+        g[k] = None
+        continue
+      if t is None:
+        t = z(*shape)
+      n = 1
+      for v in shape:
+        n *= v
+      if t.numel() != n or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+        raise ValueError("out[%r] must be a contiguous float32 tensor of %d elements on %s" % (k, n, dev))
+      g[k] = t
   d_raw = torch.empty((B, S, O, D), dtype=torch.float32, device=dev)
   v_raw = as_device_tensor(v_raw, dev)
   d_out = None if d_out is None else as_device_tensor(d_out, dev)

@@ -144,43 +144,63 @@ class RoutingStack:
   # -- training step pieces (BASELINE.json cfg-4) ------------------------------------------
   def forward_train(self, emb, dropout_masks=None):
     """Forward that keeps what the backward needs (layer inputs, pre-LayerNorm capsules,
-    dropout masks).  Returns logits [B,S,class_n]."""
+    dropout masks): one srf_route_stack_fwd call with every layer's outputs requested (the fused
+    layer-wavefront kernel where the mode and shape allow it).  Returns logits [B,S,class_n]."""
     emb = routing.as_device_tensor(emb, self.device)
     if dropout_masks is None and self.inn_dropout > 0:
       dropout_masks = self.make_dropout_masks(emb.shape[0], emb.shape[1])
     args = self.layer_args(dropout_masks)
-    self._saved = []
-    x, logits = emb, None
-    for a in args:
-      caps, lg, raw = routing.route_layer_fwd_train(x, a, self.handle)
-      self._saved.append((x, a, raw))
-      x, logits = caps, lg
+    logits, caps, raws = routing.route_stack_fwd_train(emb, args, self.handle)
+    self._saved = [(emb if i == 0 else caps[i - 1], a, raws[i]) for i, a in enumerate(args)]
+    self._saved_caps = caps
     return logits
 
-  def backward(self, d_logits, need_d_emb=True):
+  def backward(self, d_logits, need_d_emb=True, out=None, after_layer=None):
     """Backward through the routing stack of the last forward_train.  Returns
-    ({parameter name: gradient}, d_emb)."""
-    grads, d_out, n = {}, None, len(self._saved)
-    for i in reversed(range(n)):
-      x, a, raw = self._saved[i]
-      g = routing.route_layer_bwd(x, a, raw, d_out=d_out, d_logits=d_logits if i == n - 1 else None,
-                                  need_d_emb=need_d_emb or i > 0, handle=self.handle)
-      grads["W%d" % i], grads["b%d" % i] = g["dW"], g["dbias"]
-      grads["ln_mid%d/gamma" % (i + 1)], grads["ln_mid%d/beta" % (i + 1)] = g["dgamma"], g["dbeta"]
-      if i == n - 1:
-        grads["ln_output/gamma"], grads["ln_output/beta"] = g["dhead_gamma"], g["dhead_beta"]
-      d_out = g["d_emb"]
-    self._saved = []
+    ({parameter name: gradient}, d_emb).  Default: ONE srf_route_stack_bwd call.  With `out`
+    ({parameter name: zeroed tensor to accumulate into}, e.g. views of a flat gradient buffer) and /
+    or `after_layer(i)` (called once layer i's gradients are enqueued, last layer first -- the
+    data-parallel step launches that layer's all-reduce there) the layers are walked one
+    srf_route_layer_bwd call at a time."""
+    n = len(self._saved)
+    names = lambda i: {"dW": "W%d" % i, "dbias": "b%d" % i, "dgamma": "ln_mid%d/gamma" % (i + 1),
+                       "dbeta": "ln_mid%d/beta" % (i + 1), "dhead_gamma": "ln_output/gamma",
+                       "dhead_beta": "ln_output/beta"}
+    grads, d_out = {}, None
+    if out is None and after_layer is None:
+      per_layer = routing.route_stack_bwd(self._saved[0][0], [a for _, a, _ in self._saved], self._saved_caps,
+                                          [r for _, _, r in self._saved], d_logits, need_d_emb=need_d_emb,
+                                          handle=self.handle)
+      for i, g in enumerate(per_layer):
+        for k, nm in names(i).items():
+          if g[k] is not None:
+            grads[nm] = g[k]
+      d_out = per_layer[0]["d_emb"]
+    else:
+      for i in reversed(range(n)):
+        x, a, raw = self._saved[i]
+        o_i = None if out is None else {k: out.get(nm) for k, nm in names(i).items()}
+        g = routing.route_layer_bwd(x, a, raw, d_out=d_out, d_logits=d_logits if i == n - 1 else None,
+                                    need_d_emb=need_d_emb or i > 0, handle=self.handle, out=o_i)
+        for k, nm in names(i).items():
+          if g[k] is not None:
+            grads[nm] = g[k]
+        d_out = g["d_emb"]
+        if after_layer is not None:
+          after_layer(i)
+    self._saved, self._saved_caps = [], []
     return grads, d_out
 
-  def ctc_train_step_grads(self, emb, labels, input_lengths, label_lengths, dropout_masks=None):
+  def ctc_train_step_grads(self, emb, labels, input_lengths, label_lengths, dropout_masks=None,
+                           grad_scale: float = 1.0, out=None, after_layer=None):
     """fwd + CTC loss + bwd (tfsr/trainer_sr.py:56-71), all in the CUDA library (CTC loss:
-    srf_ctc_loss, blank = class_n - 1).  Returns (summed loss, grads, d_emb)."""
+    srf_ctc_loss, blank = class_n - 1).  Returns (summed loss, grads, d_emb); the gradients are
+    those of grad_scale * loss (1/global_batch = tf.nn.compute_average_loss, trainer_sr.py:67-68)."""
     from . import training
     logits = self.forward_train(emb, dropout_masks)
     loss, d_logits = training.ctc_loss(logits, labels, input_lengths, label_lengths,
-                                       blank=self.class_n - 1, handle=self.handle)
-    grads, d_emb = self.backward(d_logits)
+                                       blank=self.class_n - 1, grad_scale=grad_scale, handle=self.handle)
+    grads, d_emb = self.backward(d_logits, out=out, after_layer=after_layer)
     return loss.sum(), grads, d_emb
 
 

@@ -111,29 +111,62 @@ class TrainStep:
                warmup_steps: float = 1200.0, group=None):
     self.stack, self.global_batch, self.group = stack, int(global_batch), group
     self.k, self.d_model, self.warmup_steps = k, d_model, warmup_steps
-    self.names = [n for n, _ in stack.named_parameters()]
-    self.opt = FlatAdam([t for _, t in stack.named_parameters()], handle=stack.handle)
-    views = dict(zip(self.names, self.opt.views))
     n = len(stack.shapes)
+    # flat buffers ordered LAYER BY LAYER (W, bias, LayerNorm of layer i contiguous; the head's
+    # LayerNorm rides with the last layer), so that the gradient of a layer is one contiguous slice
+    # whose all-reduce starts as soon as that layer's backward is enqueued
+    named = dict(stack.named_parameters())
+    self.names, self.layer_slices, off = [], [], 0
+    for i in range(n):
+      group_names = ["W%d" % i, "b%d" % i, "ln_mid%d/gamma" % (i + 1), "ln_mid%d/beta" % (i + 1)]
+      if i == n - 1:
+        group_names += ["ln_output/gamma", "ln_output/beta"]
+      size = sum(named[nm].numel() for nm in group_names)
+      self.layer_slices.append((off, off + size))
+      off += size
+      self.names += group_names
+    if set(self.names) != set(named):
+      raise ValueError("unexpected parameters: %s" % sorted(set(named) ^ set(self.names)))
+    self.opt = FlatAdam([named[nm] for nm in self.names], handle=stack.handle)
+    views = dict(zip(self.names, self.opt.views))
     stack.wgt = [views["W%d" % i] for i in range(n)]
     stack.bias = [views["b%d" % i] for i in range(n)]
     stack.ln_gamma = [views["ln_mid%d/gamma" % (i + 1)] for i in range(n)]
     stack.ln_beta = [views["ln_mid%d/beta" % (i + 1)] for i in range(n)]
     stack.lno_gamma, stack.lno_beta = views["ln_output/gamma"], views["ln_output/beta"]
     stack.mark_weights_changed()
+    self.gflat = torch.zeros_like(self.opt.flat)
+    self.gviews, off = {}, 0
+    for nm, sz in zip(self.names, self.opt.sizes):
+      self.gviews[nm] = self.gflat[off:off + sz]
+      off += sz
     self.iteration = 0
 
   def step(self, emb, labels, input_lengths, label_lengths, dropout_masks=None):
     """Returns the summed CTC loss of this rank's utterances (device scalar)."""
     import torch.distributed as dist
     self.iteration += 1
-    loss, grads, _ = self.stack.ctc_train_step_grads(emb, labels, input_lengths, label_lengths,
-                                                     dropout_masks=dropout_masks)
-    flat = torch.cat([grads[k].reshape(-1) for k in self.names]).mul_(1.0 / self.global_batch)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+    self.gflat.zero_()
+    works = []
+
+    def after_layer(i):
+      # this layer's gradient slice is complete on the compute stream: its sum-all-reduce runs on the
+      # collective's own stream while the layers below are still in their backward
+      # (trainer_sr.py:70-71 all-reduces inside apply_gradients, after the whole tape)
+      if distributed:
+        lo, hi = self.layer_slices[i]
+        works.append(dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    # the loss is pre-scaled by 1/global_batch (trainer_sr.py:58,67-68) inside the CTC kernel
+    loss, _, _ = self.stack.ctc_train_step_grads(emb, labels, input_lengths, label_lengths,
+                                                 dropout_masks=dropout_masks,
+                                                 grad_scale=1.0 / self.global_batch, out=self.gviews,
+                                                 after_layer=after_layer)
+    for w in works:
+      w.wait()
     # Keras evaluates the schedule at optimizer.iterations BEFORE the increment (0 on the first
     # apply_gradients: the first learning rate is 0); only Adam's bias correction uses iterations+1
-    self.opt.step(flat, warmup_lr(self.iteration - 1, self.k, self.d_model, self.warmup_steps))
+    self.opt.step(self.gflat, warmup_lr(self.iteration - 1, self.k, self.d_model, self.warmup_steps))
     self.stack.mark_weights_changed()
     return loss

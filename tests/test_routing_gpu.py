@@ -566,6 +566,12 @@ def test_bench_mode_full_size_cfg3_parity(bench_mode):
   emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(5)).cuda()
   exact = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, 1, True, seed=9, uhat_mode="fp32")
   fast = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, 1, True, seed=9, uhat_mode=bench_mode)
+  # non-trivial LayerNorm parameters like the identity-held stack tests (gamma = 1, beta = 0 leaves the
+  # 31 untrained classes of the head at near-equal logits)
+  p_init = o.init_params(o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1), class_n, seed=9,
+                         random_ln=True)
+  exact.load_oracle_params(p_init)
+  fast.load_oracle_params(p_init)
   a = fast.forward(emb)
   a2 = fast.forward(emb)
   torch.cuda.synchronize()
@@ -581,12 +587,12 @@ def test_bench_mode_full_size_cfg3_parity(bench_mode):
   # 1125 frames compared here, so full-length strings may differ by single tokens.  The shorter
   # stacks of test_fused_stack_wavefront_matches_oracle_and_greedy_ctc and the causal prefix below
   # are held to identity; here the bar is the frame-level agreement and an edit distance of at
-  # most 1 % of the tokens of an utterance.  (The 1e-4 class, uhat_mode fp32x3, is identical throughout.)
+  # most two tokens per utterance.  (The 1e-4 class, uhat_mode fp32x3, is identical throughout.)
   agree = (a[sl].argmax(-1) == e_sl.argmax(-1)).float().mean().item()
   assert agree > 0.99, agree
   lens = [S, S - 7, S - 100]
   for got, want in zip(o.greedy_ctc(a[sl].cpu(), lens), o.greedy_ctc(e_sl.cpu(), lens)):
-    assert _edit_distance(got, want) <= max(1, len(want) // 100)     # strings of ~300 tokens
+    assert _edit_distance(got, want) <= 2                            # strings of ~70 tokens
   p = o.StackParams([w.cpu() for w in exact.wgt], [b.cpu() for b in exact.bias],
                     [g.cpu() for g in exact.ln_gamma], [b.cpu() for b in exact.ln_beta],
                     exact.lno_gamma.cpu(), exact.lno_beta.cpu())

@@ -126,3 +126,54 @@ def test_native_train_step_reduces_the_loss():
     opt.step(flat, 0.01)
     losses.append(loss.item())
   assert losses[-1] < 0.8 * losses[0], losses
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16", "bf16"])
+def test_stack_backward_one_call_equals_layer_loop_and_trainstep_buffers(mode):
+  """srf_route_stack_bwd (one C call) against the same backward walked layer by layer into the views
+  of a flat, layer-ordered gradient buffer (what TrainStep does to launch a layer's all-reduce while
+  the layers below are still in their backward): bit-identical; and a TrainStep on top of it equals
+  Adam applied to those gradients."""
+  from srf_b200 import RoutingStack, training
+  L, PH, CH, cls, DIM, B, S = 3, 12, 8, 9, 8, 3, 10
+  stack = RoutingStack(L, PH, CH, cls, DIM, DIM, DIM, 1, 1, 1, True, seed=2, inn_dropout=0.1, uhat_mode=mode)
+  g = torch.Generator().manual_seed(5)
+  emb = torch.randn(B, S, PH, DIM, generator=g).cuda()
+  labels = torch.randint(1, cls - 1, (B, 3), generator=g).cuda()
+  in_len, lab_len = torch.tensor([S, S - 2, S - 1]).cuda(), torch.full((B,), 3).cuda()
+  masks = stack.make_dropout_masks(B, S, generator=None)
+  loss_a, grads_a, d_emb_a = stack.ctc_train_step_grads(emb, labels, in_len, lab_len, dropout_masks=masks,
+                                                        grad_scale=0.5)
+  order = []
+  views = {n: torch.zeros_like(t).reshape(-1) for n, t in stack.named_parameters()}
+  loss_b, grads_b, d_emb_b = stack.ctc_train_step_grads(emb, labels, in_len, lab_len, dropout_masks=masks,
+                                                        grad_scale=0.5, out=views, after_layer=order.append)
+  torch.cuda.synchronize()
+  assert order == [2, 1, 0]
+  assert torch.equal(loss_a, loss_b) and torch.equal(d_emb_a, d_emb_b)
+  assert set(grads_a) == set(views)
+  for n in views:
+    assert grads_b[n].data_ptr() == views[n].data_ptr()                 # written in place
+    if n[0] in "Wb":      # dW / dbias are atomics-free; the LayerNorm sums leave with one atomic per CTA
+      assert torch.equal(grads_a[n].reshape(-1), views[n]), n
+    else:
+      assert torch.allclose(grads_a[n].reshape(-1), views[n], rtol=1e-5, atol=1e-6), n
+    assert views[n].abs().sum().item() > 0, n
+  # TrainStep: flat buffers ordered layer by layer; one step = Adam on the gradient of loss / global_batch
+  p0 = {n: t.detach().clone() for n, t in stack.named_parameters()}
+  tr = training.TrainStep(stack, global_batch=2, warmup_steps=4.0)
+  assert tr.layer_slices[0][0] == 0 and tr.layer_slices[-1][1] == tr.opt.flat.numel()
+  assert tr.names[:4] == ["W0", "b0", "ln_mid1/gamma", "ln_mid1/beta"] and tr.names[-1] == "ln_output/beta"
+  tr.step(emb, labels, in_len, lab_len, dropout_masks=masks)             # first learning rate is 0 (Keras)
+  for n, t in stack.named_parameters():
+    assert torch.equal(t, p0[n]), n
+  tr.step(emb, labels, in_len, lab_len, dropout_masks=masks)
+  torch.cuda.synchronize()
+  lr = training.warmup_lr(1, 0.5, 256.0, 4.0)
+  for n, t in stack.named_parameters():
+    gr = grads_a[n].reshape(t.shape)        # gradient of 0.5 * loss = loss / global_batch, unchanged weights
+    m, v = 0.1 * gr, 0.02 * gr * gr
+    m = 0.9 * m + 0.1 * gr
+    v = 0.98 * v + 0.02 * gr * gr
+    want = p0[n] - lr * math.sqrt(1 - 0.98 ** 2) / (1 - 0.9 ** 2) * m / (v.sqrt() + 1e-9)
+    assert torch.allclose(t, want, rtol=2e-4, atol=1e-6), n

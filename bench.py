@@ -445,6 +445,33 @@ def main():
           "unit": "routing frames/s", "kernel": st2.handle.last_kernel.split(" ")[0],
           "note": "inputs resident" + ("; 1e-4 tolerance class" if mode == "fp32x3" else "")}
       del st2
+  if world == 1 and not args.no_also:
+    # ---- next-1 row: the native capsulation front-end feeding the hot path (fbank -> logits) ----
+    import types
+    from srf_b200 import SequenceRouter
+    cfg = types.SimpleNamespace(
+        model_initializer="fan_avg", model_conv_layer_num=2, feat_dim=123, model_conv_filter_num=64,
+        model_encoder_num=w["L"], model_caps_iter=w["iters"], model_caps_window_lpad=w["lpad"],
+        model_caps_window_rpad=w["rpad"], model_caps_context=w["sdr"], model_caps_primary_num=w["PH"],
+        model_caps_primary_dim=w["DIM"], model_caps_convolution_num=w["CH"], model_caps_convolution_dim=w["DIM"],
+        model_caps_class_dim=w["DIM"], train_inp_dropout=0.1, train_inn_dropout=0.1)
+    model = SequenceRouter(cfg, None, w["class_n"], device=dev, seed=0, uhat_mode=args.uhat)
+    gfe = torch.Generator().manual_seed(7)
+    fbank = torch.randn(B, w["T"], 123, generator=gfe).to(dev)
+    flen = torch.cat([torch.tensor([w["T"]]), (w["T"] * (0.6 + 0.4 * torch.rand(B - 1, generator=gfe))).long()]).int().to(dev)
+    for _ in range(2):
+      model(fbank, input_lengths=flen)
+    ms_fe = timed(lambda i: model.capsulate(fbank, flen), 5) / 5
+    ms_all = timed(lambda i: model(fbank, input_lengths=flen), 5) / 5
+    conv_flops = 2.0 * B * (((w["T"] + 1) // 2) * 62 * 9 * 1 * 128 + S * 31 * 9 * 64 * 128) + 2.0 * B * S * 31 * 64 * w["PH"]
+    line["also"]["frontend_%s" % args.workload] = {
+        "workload": "capsulation front-end (srf_capsulate_fwd: 2 CNN-FE stages with 64 filters, Dense(%d), encaps "
+                    "maxout, squash, ln_input) on fbank [%d,%d,123], then the routing stack" % (w["PH"], B, w["T"]),
+        "frontend_ms": ms_fe, "fbank_to_logits_ms": ms_all,
+        "fbank_frames_per_sec": B * w["T"] / (ms_all / 1e3),
+        "frontend_fp32_tflops": conv_flops / (ms_fe / 1e3) / 1e12,
+        "note": "FP32 CUDA-core kernels (1e-4 class); inputs resident"}
+    del model
   if rank == 0 and not args.no_cpu_baseline and world == 1:
     n_utts, n_frames = cpu_sample_shape(w)
     fps, dt = cpu_reference_run(w, n_utts, n_frames, repeats=2)

@@ -687,7 +687,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
     // alternate capsules.  Both walk the whole tile stream: a W stage is handed back to the
     // producer by a tcgen05.commit of EACH issuer (w_empty counts 2), which arrives once that
     // thread's own MMAs on the stage have retired (at once if it had none).
-    if (lane == 0) {
+    // ONE elected thread runs the issuer: inside an elect.sync-guarded region ptxas knows a single thread
+    // is active and emits plain UTCHMMA instructions; under `lane == 0` it wraps every tcgen05.mma in an
+    // ELECT / BRA.U.ANY serialisation loop (~100 clk of dependent uniform-datapath latency per MMA)
+    if (ptx::elect_one()) {
       const int me = swarp;
       const uint32_t idesc = F16 ? ptx::make_idesc_f16(128, FZ_N) : ptx::make_idesc_tf32(128, FZ_N);
       // K-major no-swizzle descriptors: low word = start address >> 4 | LBO >> 4 << 16, high word =

@@ -1387,6 +1387,10 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   p.dp = (L->d + 3) & ~3;
   p.FS = 1;
   p.fps = 0;
+  // the reduced-precision modes differentiate a TF32-class function: their phase B runs on the tensor
+  // cores; FP32 and FP32X3 (the 1e-4 class) keep the FP32 CUDA-core contraction
+  p.tc_phase_b = (L->uhat_mode == SRF_UHAT_TF32 || L->uhat_mode == SRF_UHAT_BF16 || L->uhat_mode == SRF_UHAT_F16) &&
+                 !getenv("SRF_BWD_NO_TC");
   p.cbuf = p.gabuf = p.gtT = p.vaT = p.dxw = p.dwp = nullptr;
   if (p.split) {
     p.FS = srf::dwdx_frame_splits(p, h->max_smem, h->num_sms);

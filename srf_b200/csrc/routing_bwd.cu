@@ -803,9 +803,14 @@ static bool dwdx_plan(const BwdParams& p, int max_smem, DwdxPlan* pl) {
 }
 
 // number of frame splits phase B will use (the caller sizes dwp with it)
+bool dwdx_uses_tensor_cores(const BwdParams& p, int max_smem);
+
 int dwdx_frame_splits(const BwdParams& p, int max_smem, int num_sms) {
   DwdxPlan pl;
-  if (!dwdx_plan(p, max_smem, &pl)) return 0;
+  if (dwdx_uses_tensor_cores(p, max_smem))
+    pl.FT = 32;
+  else if (!dwdx_plan(p, max_smem, &pl))
+    return 0;
   const long long frames = (long long)p.B * p.S;
   const long long tiles = (frames + pl.FT - 1) / pl.FT;
   const int per = p.I * (p.OP / 32);
@@ -1001,6 +1006,237 @@ __global__ void __launch_bounds__(MAXT, 1) dwdx_from_saved_kernel(const BwdParam
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// phase B on the tensor cores (uhat_mode TF32 / F16 / BF16: the gradient carries the rounding class
+// of the mode anyway).  Same grid, same shared-memory tiles and the same deterministic partial-sum
+// scheme as dwdx_from_saved_kernel; the two contractions of a 32-frame tile run as warp-level
+// mma.sync.m16n8k8 TF32 with fp32 accumulation in registers:
+//   dW[(k,j)][l]  += g_u^T [(k,j)] [ft] . x  [ft] [l]      M = 32 D rows, N = d+1 (bias column), K = 32 frames
+//   dx [ft] [l]    = g_u   [ft] [(k,j)] . W_i [(k,j)] [l]  M = 32 frames, N = d,   K = 32 D
+// 8 warps; warp w owns the 16-row blocks w, w+8, ... of dW (all tiles of the CTA's frame split
+// accumulate in its registers) and the K steps w, w+8, ... of dx (partials folded through shared memory).
+// g_u, x and W_i are rounded to TF32 (rna) when they are written to shared memory.
+// ---------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+        "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+constexpr int DWM_FT = 32, DWM_WARPS = 8;
+}  // namespace
+
+size_t dwdx_mma_smem_bytes(int D, int d) {
+  const int dp = (d + 3) & ~3, xrow = (d + 2) & ~1;
+  return sizeof(float) * ((size_t)32 * D * dp + (size_t)DWM_FT * (D * 36 + 4) + round4(DWM_FT * xrow) +
+                          (size_t)DWM_WARPS * DWM_FT * dp);
+}
+
+// MBW = 16-row blocks of dW per warp (2 D / 8 rounded up), NB = 8-column blocks of l
+template <int MBW, int NB>
+__global__ void __launch_bounds__(DWM_WARPS * 32, 1) dwdx_from_saved_mma_kernel(const BwdParams p) {
+  constexpr int GB = 4, FT = DWM_FT, NT = DWM_WARPS * 32;
+  extern __shared__ __align__(16) float sm[];
+  const int D = p.D, d = p.d, dp = p.dp, R = p.iters, O = p.O, I = p.I, OP = p.OP, Tu = p.Tu;
+  const int d1 = d + 1, GS = D * 36 + 4;
+  const int xrow = (d + 2) & ~1;
+  float* Ws = sm;                          // [32][D][dp]
+  float* gus = Ws + 32 * D * dp;           // [FT][GS]: g_u[ft][k][j] at k*36 + j
+  float* xs = gus + FT * GS;               // [FT][xrow]
+  float* dxs = xs + round4(FT * xrow);     // [warps][FT][dp]
+  const int i = blockIdx.x, fs = blockIdx.y, q = blockIdx.z, OPL = gridDim.z;
+  const int jbase = q * 32;
+  const int nj = (O - jbase) < 32 ? (O - jbase) : 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int w = i / p.H, hc = i - w * p.H;
+  const long long frames = (long long)p.B * p.S;
+  const long long f_lo = (long long)fs * p.fps;
+  const long long f_hi = (f_lo + p.fps) < frames ? (f_lo + p.fps) : frames;
+
+  for (int e = tid; e < 32 * D * dp; e += NT) {
+    const int l = e % dp, jk = e / dp, k = jk % D, j = jk / D;
+    float v = 0.f;
+    if (j < nj && l < d) v = p.W[(((size_t)i * O + jbase + j) * D + k) * d + l];
+    Ws[e] = to_tf32(v);
+  }
+  float acc[MBW][NB][4];
+#pragma unroll
+  for (int a = 0; a < MBW; ++a)
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  for (long long f0 = f_lo; f0 < f_hi; f0 += FT) {
+    const int nf = (int)((f_hi - f0) < FT ? (f_hi - f0) : FT);
+    // (a) window-gathered x of capsule i for the tile (+ the bias column of ones)
+    for (int e = tid; e < FT * xrow; e += NT) {
+      const int ft = e / xrow, l = e - ft * xrow;
+      float v = 0.f;
+      if (ft < nf) {
+        if (l == d) {
+          v = 1.f;
+        } else if (l < d) {
+          const long long f = f0 + ft;
+          const int b = (int)(f / p.S), s_ = (int)(f - (long long)b * p.S);
+          const int src = s_ - p.lpad + w;
+          if (src >= 0 && src < p.S) v = p.emb[(((long long)b * p.S + src) * p.H + hc) * d + l];
+        }
+      }
+      xs[e] = to_tf32(v);
+    }
+    // (b) g_u of the tile (as in dwdx_from_saved_kernel), rounded to TF32
+    {
+      const int D4 = (D + 3) >> 2, per = 32 * D4, NG = (FT + GB - 1) / GB;
+      const size_t cstride = (size_t)R * I * OP, gstride = (size_t)R * O * Tu;
+      for (int it = tid; it < NG * per; it += NT) {
+        const int grp = it / per, rem = it - grp * per;
+        const int j = rem / D4, k4 = rem - j * D4;
+        const bool jok = j < nj;
+        const int jc = jok ? j : 0;
+        const int ft0 = grp * GB;
+        const float* cb = p.cbuf + ((size_t)f0 * R * I + i) * OP + jbase + jc;
+        const float* gab = p.gabuf + ((size_t)f0 * R * I + i) * OP + jbase + jc;
+        const float* gtb = p.gtT + ((size_t)f0 * R * O + jbase + jc) * Tu + k4 * 4;
+        const float* vab = p.vaT + ((size_t)f0 * R * O + jbase + jc) * Tu + k4 * 4;
+        float4 gg[GB];
+#pragma unroll
+        for (int u = 0; u < GB; ++u) gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < R; ++r) {
+          float cv[GB], gav[GB];
+          float4 gtv[GB], vav[GB];
+#pragma unroll
+          for (int u = 0; u < GB; ++u) {
+            const int ft = (ft0 + u) < nf ? (ft0 + u) : (nf - 1);
+            const size_t oc = ft * cstride + (size_t)r * I * OP;
+            const size_t og = ft * gstride + (size_t)r * O * Tu;
+            cv[u] = __ldg(cb + oc);
+            gav[u] = __ldg(gab + oc);
+            gtv[u] = __ldg(reinterpret_cast<const float4*>(gtb + og));
+            vav[u] = __ldg(reinterpret_cast<const float4*>(vab + og));
+          }
+#pragma unroll
+          for (int u = 0; u < GB; ++u) {
+            gg[u].x = fmaf(cv[u], gtv[u].x, fmaf(gav[u], vav[u].x, gg[u].x));
+            gg[u].y = fmaf(cv[u], gtv[u].y, fmaf(gav[u], vav[u].y, gg[u].y));
+            gg[u].z = fmaf(cv[u], gtv[u].z, fmaf(gav[u], vav[u].z, gg[u].z));
+            gg[u].w = fmaf(cv[u], gtv[u].w, fmaf(gav[u], vav[u].w, gg[u].w));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+          const int ft = ft0 + u;
+          if (ft < FT) {
+            const bool ok = jok && ft < nf;
+            float* dst = gus + ft * GS + (k4 * 4) * 36 + j;
+            const float gv[4] = {gg[u].x, gg[u].y, gg[u].z, gg[u].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (k4 * 4 + c < D) dst[c * 36] = ok ? to_tf32(gv[c]) : 0.f;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // (c) dW / dbias: A[(k, j0 + row)][ft] = g_u, B[ft][l] = x
+#pragma unroll
+    for (int ks = 0; ks < FT / 8; ++ks) {
+      float b0[NB], b1[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int l = nb * 8 + g;
+        b0[nb] = l < xrow ? xs[(ks * 8 + t) * xrow + l] : 0.f;
+        b1[nb] = l < xrow ? xs[(ks * 8 + t + 4) * xrow + l] : 0.f;
+      }
+#pragma unroll
+      for (int mi = 0; mi < MBW; ++mi) {
+        const int mb = warp + DWM_WARPS * mi;
+        if (mb < 2 * D) {
+          const float* ap = gus + (ks * 8 + t) * GS + (mb >> 1) * 36 + (mb & 1) * 16 + g;
+          const float a[4] = {ap[0], ap[8], ap[4 * GS], ap[4 * GS + 8]};
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) mma_tf32_16x8x8(acc[mi][nb], a, b0[nb], b1[nb]);
+        }
+      }
+    }
+    // (d) dx: A[ft][(k, j0 + col)] = g_u, B[(k, j)][l] = W_i; this warp's share of the K steps
+    {
+      float ax[2][NB][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ax[a][b][c] = 0.f;
+      for (int ks = warp; ks < 4 * D; ks += DWM_WARPS) {
+        const int k = ks >> 2, j0 = (ks & 3) * 8;
+        float b0[NB], b1[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const int l = nb * 8 + g;
+          b0[nb] = l < dp ? Ws[((j0 + t) * D + k) * dp + l] : 0.f;
+          b1[nb] = l < dp ? Ws[((j0 + t + 4) * D + k) * dp + l] : 0.f;
+        }
+#pragma unroll
+        for (int mbx = 0; mbx < 2; ++mbx) {
+          const float* ap = gus + (mbx * 16 + g) * GS + k * 36 + j0 + t;
+          const float a[4] = {ap[0], ap[8 * GS], ap[4], ap[8 * GS + 4]};
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) mma_tf32_16x8x8(ax[mbx][nb], a, b0[nb], b1[nb]);
+        }
+      }
+#pragma unroll
+      for (int mbx = 0; mbx < 2; ++mbx)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const int l = nb * 8 + 2 * t;
+          float* o0 = dxs + ((size_t)warp * FT + mbx * 16 + g) * dp + l;
+          float* o1 = o0 + 8 * dp;
+          if (l < dp) {
+            o0[0] = ax[mbx][nb][0];
+            o1[0] = ax[mbx][nb][2];
+          }
+          if (l + 1 < dp) {
+            o0[1] = ax[mbx][nb][1];
+            o1[1] = ax[mbx][nb][3];
+          }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * dp; e += NT) {
+      const int ft = e / dp, l = e - ft * dp;
+      float s_ = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < DWM_WARPS; ++pp) s_ += dxs[((size_t)pp * FT + ft) * dp + l];
+      p.dxw[((((size_t)(f0 + ft)) * I + i) * OPL + q) * dp + l] = s_;
+    }
+    // the next tile's (a) / (b) overwrite xs / gus: every warp must be done with (c) and (d), which the
+    // barrier above guarantees; dxs is rewritten only after the next tile's first barrier
+  }
+#pragma unroll
+  for (int mi = 0; mi < MBW; ++mi) {
+    const int mb = warp + DWM_WARPS * mi;
+    if (mb >= 2 * D) continue;
+    const int k = mb >> 1, j0 = (mb & 1) * 16;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + g + (c >> 1) * 8, l = nb * 8 + 2 * t + (c & 1);
+        if (j < nj && l < d1)
+          p.dwp[((((size_t)fs * I + i) * O + jbase + j) * D + k) * d1 + l] = acc[mi][nb][c];
+      }
+  }
+}
+
 // dW += sum_fs dwp[fs][..][l < d],  dbias += sum_fs dwp[fs][..][d]
 __global__ void reduce_dwp_kernel(const BwdParams p) {
   const int d1 = p.d + 1;
@@ -1016,21 +1252,46 @@ __global__ void reduce_dwp_kernel(const BwdParams p) {
   }
 }
 
+// tensor-core phase B variant for the shape, or null: MBW covers 2 D row blocks over 8 warps, NB the
+// d+1 columns
+typedef void (*DwdxMmaKernel)(const BwdParams);
+static DwdxMmaKernel dwdx_mma_variant(int D, int d) {
+  const int mbw = (2 * D + DWM_WARPS - 1) / DWM_WARPS, nb = (d + 1 + 7) / 8;
+  if (nb > 3 || mbw > 5) return nullptr;
+  const int MB = mbw <= 2 ? 2 : (mbw <= 4 ? 4 : 5), NBc = nb <= 2 ? 2 : 3;
+  if (MB == 2) return NBc == 2 ? dwdx_from_saved_mma_kernel<2, 2> : dwdx_from_saved_mma_kernel<2, 3>;
+  if (MB == 4) return NBc == 2 ? dwdx_from_saved_mma_kernel<4, 2> : dwdx_from_saved_mma_kernel<4, 3>;
+  return NBc == 2 ? dwdx_from_saved_mma_kernel<5, 2> : dwdx_from_saved_mma_kernel<5, 3>;
+}
+
+bool dwdx_uses_tensor_cores(const BwdParams& p, int max_smem) {
+  return p.tc_phase_b && dwdx_mma_variant(p.D, p.d) != nullptr &&
+         dwdx_mma_smem_bytes(p.D, p.d) <= (size_t)max_smem;
+}
+
 cudaError_t launch_dwdx_from_saved(const BwdParams& p, int max_smem, cudaStream_t stream) {
-  DwdxPlan pl;
-  if (!dwdx_plan(p, max_smem, &pl)) return cudaErrorInvalidValue;
   dim3 grid(p.I, p.FS, p.OP / 32);
   cudaError_t e;
-  auto go = [&](auto kern) -> cudaError_t {
-    cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (ee != cudaSuccess) return ee;
-    kern<<<grid, pl.NT, pl.smem, stream>>>(p, pl.FT, pl.NC, pl.P);
-    return cudaSuccess;
-  };
-  if (pl.NT <= 384) e = go(dwdx_from_saved_kernel<384>);
-  else if (pl.NT <= 512) e = go(dwdx_from_saved_kernel<512>);
-  else e = go(dwdx_from_saved_kernel<1024>);
-  if (e != cudaSuccess) return e;
+  if (dwdx_uses_tensor_cores(p, max_smem)) {
+    DwdxMmaKernel kern = dwdx_mma_variant(p.D, p.d);
+    const size_t smem = dwdx_mma_smem_bytes(p.D, p.d);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, DWM_WARPS * 32, smem, stream>>>(p);
+  } else {
+    DwdxPlan pl;
+    if (!dwdx_plan(p, max_smem, &pl)) return cudaErrorInvalidValue;
+    auto go = [&](auto kern) -> cudaError_t {
+      cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (ee != cudaSuccess) return ee;
+      kern<<<grid, pl.NT, pl.smem, stream>>>(p, pl.FT, pl.NC, pl.P);
+      return cudaSuccess;
+    };
+    if (pl.NT <= 384) e = go(dwdx_from_saved_kernel<384>);
+    else if (pl.NT <= 512) e = go(dwdx_from_saved_kernel<512>);
+    else e = go(dwdx_from_saved_kernel<1024>);
+    if (e != cudaSuccess) return e;
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long long n = (long long)p.I * p.O * p.D * (p.d + 1);

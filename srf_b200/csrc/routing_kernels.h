@@ -77,6 +77,7 @@ struct BwdParams {
   int FS;          // frame splits of phase B; partial sums go to dwp
   int fps;         // frames per split
   float* dwp;      // [FS][I][O][D][d+1]   partial dW (l < d) and dbias (l == d)
+  int tc_phase_b;  // 1: phase B contractions on the tensor cores (TF32 mma.sync; the reduced-precision modes)
   // streamed u_hat (uhat_mode TF32 / BF16): the BPTT kernel reads the tcgen05 GEMM's output
   const void* u;
   int halfB;

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRF_B200_VERSION 200 /* major*10000 + minor*100 + patch */
+#define SRF_B200_VERSION 210 /* major*10000 + minor*100 + patch */
 
 typedef struct srf_handle srf_handle;
 
@@ -103,7 +103,7 @@ int srf_destroy(srf_handle* h);
 const char* srf_last_error(const srf_handle* h);
 
 /*
- * Kernel selection.  uhat_mode TF32 / FP32X3 run the FUSED routing kernel (routing_fused.cu: u_hat is
+ * Kernel selection.  uhat_mode TF32 / F16 / FP32X3 run the FUSED routing kernel (routing_fused.cu: u_hat is
  * produced by tcgen05.mma into TMEM and consumed there, an SDR stack is ONE persistent launch over all
  * layers) when the shape is supported (d % 4 == 0, D <= 20, O <= 64, 16-byte aligned emb) and the
  * library's policy expects it to be faster than the two-kernel path (materialised u_hat); BF16 always

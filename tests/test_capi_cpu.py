@@ -26,7 +26,7 @@ def test_python_binding_lists_every_symbol(built_lib):
   from srf_b200 import _lib
   assert sorted(_lib.EXPORTS) == _declared_symbols()
   lib = _lib.load()
-  assert lib.srf_version() == 200
+  assert lib.srf_version() == 210
 
 
 def test_layer_desc_matches_header_layout():

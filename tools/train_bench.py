@@ -30,7 +30,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--batch", type=int, default=64, help="global batch (utterances)")
   ap.add_argument("--frames", type=int, default=375, help="routing frames per utterance")
-  ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "bf16"])
+  ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "f16", "bf16", "fp32x3"])
   ap.add_argument("--workload", default="cfg3")
   args = ap.parse_args()
   rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -79,7 +79,7 @@ def main():
         "metric": "SRF-SDR training-step routing frames/sec (fwd + CTC + bwd + grad all-reduce + Adam)",
         "value": args.batch * S / (ms_step / 1e3), "unit": "routing frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong", "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "dtype": {"fp32": "f32", "fp32x3": "f32"}.get(args.uhat, args.uhat), "data": "synthetic",
         "config": {"workload": "cfg4: " + w["desc"] + ", training step", "global_batch": args.batch,
                    "routing_frames_per_utterance": S, "uhat": args.uhat,
                    "parallelism": "dp%d (utterance shards, NCCL all-reduce of %d gradient floats)"

@@ -8,6 +8,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_void_p)
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrf_b200.so")
+# developer override: another build of the SAME library (e.g. with the clock64 phase timers compiled in)
+LIB_PATH = os.environ.get("SRF_B200_LIB", LIB_PATH)
 
 SRF_UHAT_FP32, SRF_UHAT_TF32, SRF_UHAT_BF16, SRF_UHAT_FP32X3, SRF_UHAT_F16 = 0, 1, 2, 3, 4
 UHAT_MODES = {"fp32": SRF_UHAT_FP32, "tf32": SRF_UHAT_TF32, "bf16": SRF_UHAT_BF16,

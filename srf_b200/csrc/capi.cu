@@ -1092,9 +1092,27 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
     while (nwst > 3 && srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst, G * wpair) > (size_t)h->max_smem) --nwst;
     if (srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst, G * wpair) <= (size_t)h->max_smem) break;
   }
+  // Capsule-sized stages: when three stages of one capsule's tiles (NT x wpair) fit, the kernel runs ONE MMA
+  // issuer and a dedicated W producer, and a stage is released by the capsule's own commit (no second
+  // issuer's book-keeping, no commit per stage).  SRF_FUSED_CAPSTAGE=0 keeps the tile-granular ring.
+  int capstage = 0;
+  {
+    const char* ev = getenv("SRF_FUSED_CAPSTAGE");
+    const size_t cb = (size_t)T4 * OPLM * wpair;
+    // (small capsules keep the tile-granular ring: its stages bundle several capsules into ~48 KB copies,
+    // and the L2 -> shared-memory rate follows the bytes per barrier round trip; cfg-2: 16 KB per capsule)
+    const bool big = cb >= 32768 || (ev && ev[0] == '1');
+    if (big && !(ev && ev[0] == '0') && srf::route_fused_smem_bytes(OPLM, KCmax, kmode, 3, cb) <= (size_t)h->max_smem) {
+      capstage = 1;
+      G = T4 * OPLM;
+      nwst = 3;
+      while (nwst < 6 && srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst + 1, cb) <= (size_t)h->max_smem) ++nwst;
+    }
+  }
   // the MMA issuers address a capsule's tiles through at most three ring stages
-  if (G < 1 || T4 * OPLM >= 2 * G + 2) return FUSED_FALLBACK;   // the two-kernel path takes this shape
+  if (G < 1 || (!capstage && T4 * OPLM >= 2 * G + 2)) return FUSED_FALLBACK;   // the two-kernel path takes this shape
   const size_t smem = srf::route_fused_smem_bytes(OPLM, KCmax, kmode, nwst, G * wpair);
+  p.capstage = capstage;
   p.gtiles = G;
   p.wstage_bytes = (int)(G * wpair);
   p.xtile_bytes = KCmax * 32 * 16;
@@ -1136,6 +1154,7 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
            "tiles smem=%zu",
            T4, OPLM, parts == 2 ? "3xTF32" : (parts == 0 ? "f16" : "tf32"), sdr ? "SDR-wavefront" : "DR", n, grid, ngroups, rounds,
            maxC, nwst, G, smem);
+  if (capstage) strncat(nm, " capstage", sizeof(nm) - strlen(nm) - 1);
   h->last_kernel = nm;
   return 0;
 }

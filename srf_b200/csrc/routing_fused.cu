@@ -140,7 +140,10 @@ constexpr int FZ_MATH_WARPS = 8;
 constexpr int FZ_THREADS = 384;          // 4 service warps + 8 math warps
 constexpr int FZ_CAP_RING = 8;           // capsule-completion barriers (>= x ring depth and TMEM buffers)
 constexpr int FZ_STG = 4;                // fp32 staging slots of the FP16-image x loader (3 capsules of lookahead)
-constexpr int FZ_XST_MAX = 8;            // x-tile ring depth (tf32; the 3 x TF32 build keeps two images: 4)
+#ifndef SRF_FZ_XST
+#define SRF_FZ_XST 8
+#endif
+constexpr int FZ_XST_MAX = SRF_FZ_XST;            // x-tile ring depth (tf32; the 3 x TF32 build keeps two images: 4)
 constexpr long long FZ_TIMEOUT = 6000000000ll;  // ~3 s of SM clocks
 
 enum { BAR_TEAM0 = 1, BAR_MATH = 5 };
@@ -690,7 +693,111 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
     // ONE elected thread runs the issuer: inside an elect.sync-guarded region ptxas knows a single thread
     // is active and emits plain UTCHMMA instructions; under `lane == 0` it wraps every tcgen05.mma in an
     // ELECT / BRA.U.ANY serialisation loop (~100 clk of dependent uniform-datapath latency per MMA)
-    if (ptx::elect_one()) {
+    if (p.capstage) {
+      // ---- capsule-sized ring stages (the layout the host picks when three of them fit) ----
+      // warp 8: the ONE MMA issuer.  Per capsule: x tile full, TMEM buffer free, W stage full, NT x K/16
+      // MMAs from straight-line code, ONE tcgen05.commit (cap_done) that tells the routing warps "TMEM
+      // buffer full", the x loader "x slot free" and the W producer "ring stage free".  No second issuer
+      // whose books must be kept, no commit per ring stage.
+      // warp 9: the W producer.  Stage n % NWST is refilled with capsule n's tiles (one bulk copy from L2)
+      // as soon as capsule n - NWST has retired; weights do not depend on the recurrence, so the ring
+      // runs ahead across time steps.
+      if (swarp == 0) {
+        if (ptx::elect_one()) {
+          const uint32_t idesc = F16 ? ptx::make_idesc_f16(128, FZ_N) : ptx::make_idesc_tf32(128, FZ_N);
+          constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+          const uint32_t a_lo0 = ((ptx::smem_u32(sW) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+          const uint32_t b_lo0 = ((ptx::smem_u32(sX) >> 4) & 0x3FFFu) | (((FZ_N * 16u) >> 4) << 16);
+          const uint32_t blo_lo0 = ((ptx::smem_u32(sXlo) >> 4) & 0x3FFFu) | (((FZ_N * 16u) >> 4) << 16);
+          const uint32_t wstage16 = wstage >> 4, wpair16 = wpair >> 4, wtile16 = wtile >> 4, xtile16 = xtile >> 4;
+          const int nks = KC / 2;
+          const int nt = u_nt;
+          uint32_t n = 0;
+#ifdef SRF_FUSED_TIMERS
+          unsigned* trace = nullptr;
+          if (p.dbg && (blockIdx.x == 0 || blockIdx.x == 80))
+            trace = reinterpret_cast<unsigned*>(p.dbg) + 6000 + (blockIdx.x == 0 ? 0 : 3072);
+          unsigned ncap_tr = 0;
+#define FZ_MK1(slot) if (trace && ncap_tr < 512) trace[ncap_tr * 6 + (slot)] = (unsigned)clock();
+#else
+#define FZ_MK1(slot)
+#endif
+          for (int it = 0; it < p.rounds; ++it) {
+            const FusedItem item = p.items[(size_t)it * gridDim.x + blockIdx.x];
+            if (item.layer < 0) continue;
+            const int total = nsteps * iters * u_ncap;
+            for (int cc = 0; cc < total; ++cc, ++n) {
+              const uint32_t xs = n % (uint32_t)XST, buf = n % (uint32_t)NBUF, ws = n % (uint32_t)NWST;
+              FZ_MK1(0)
+              wt.mbar(x_full + 8u * xs, (n / XST) & 1, 104);
+              ptx::fence_proxy_async();   // cp.async / st.shared wrote the tile through the generic proxy
+              FZ_MK1(1)
+              wt.mbar(t_empty + 8u * buf, ((n / NBUF) & 1) ^ 1, 105);
+              FZ_MK1(2)
+              wt.mbar(w_full + 8u * ws, (n / (uint32_t)NWST) & 1, 106);
+              FZ_MK1(5)
+              ptx::tc_fence_after();
+              const uint32_t d_base = tmem_base + buf * (uint32_t)TCOLS;
+              const uint32_t b_lo = b_lo0 + xs * xtile16, blo_lo = blo_lo0 + xs * xtile16;
+              const uint32_t a_base = a_lo0 + ws * wstage16;
+              if (nt == NT && (nks == 2 || nks == 3 || nks == 5 || (F16 && nks == 1))) {
+                uint32_t al[NT];
+#pragma unroll
+                for (int m = 0; m < NT; ++m) al[m] = a_base + (uint32_t)m * wpair16;
+                if (nks == 3) mma_issue_capsule<NT, 3, X3, F16>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else if (nks == 2) mma_issue_capsule<NT, 2, X3, F16>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else if (F16 && nks == 1) mma_issue_capsule<NT, 1, false, true>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+                else mma_issue_capsule<NT, 5, X3, F16>(d_base, al, b_lo, blo_lo, wtile16, DESC_HI, idesc);
+              } else {
+#pragma unroll
+                for (int m = 0; m < NT; ++m) {
+                  if (m < nt) {
+                    const uint32_t a_lo = a_base + (uint32_t)m * wpair16;
+#pragma unroll
+                    for (int ks = 0; ks < 5; ++ks) {
+                      if (ks < nks) {
+                        mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, ks > 0);
+                        if (X3) {
+                          mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo + wtile16 + ks * 256, b_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                          mma_tf32_lo<F16>(d_base + m * FZ_N, a_lo + ks * 256, blo_lo + ks * (2 * FZ_N), DESC_HI, idesc, true);
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+              FZ_MK1(3)
+              mma_commit_a(cap_done + 8u * (n % (uint32_t)FZ_CAP_RING));
+              FZ_MK1(4)
+#ifdef SRF_FUSED_TIMERS
+              ++ncap_tr;
+#endif
+            }
+          }
+        }
+      } else if (ptx::elect_one()) {
+        const uint32_t sW_a = ptx::smem_u32(sW);
+        const uint64_t w_policy = l2_policy_evict_last();
+        uint32_t n = 0;
+        for (int it = 0; it < p.rounds; ++it) {
+          const FusedItem item = p.items[(size_t)it * gridDim.x + blockIdx.x];
+          if (item.layer < 0) continue;
+          const uint32_t bytes = (uint32_t)u_nt * wpair;
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.layers[item.layer].Wf) + (size_t)item.i_lo * bytes;
+          const int npass = nsteps * iters;
+          for (int ps = 0; ps < npass; ++ps)
+            for (int cc = 0; cc < u_ncap; ++cc, ++n) {
+              const uint32_t ws = n % (uint32_t)NWST;
+              if (n >= (uint32_t)NWST) {
+                const uint32_t prev = n - (uint32_t)NWST;   // the stage's previous tenant has retired
+                wt.mbar(cap_done + 8u * (prev % FZ_CAP_RING), (prev / FZ_CAP_RING) & 1, 103);
+              }
+              mbar_expect_tx_a(w_full + 8u * ws, bytes);
+              bulk_g2s_a(sW_a + ws * wstage, wsrc + (size_t)cc * bytes, bytes, w_full + 8u * ws, w_policy);
+            }
+        }
+      }
+    } else if (ptx::elect_one()) {
       const int me = swarp;
       const uint32_t idesc = F16 ? ptx::make_idesc_f16(128, FZ_N) : ptx::make_idesc_tf32(128, FZ_N);
       // K-major no-swizzle descriptors: low word = start address >> 4 | LBO >> 4 << 16, high word =
@@ -970,7 +1077,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               mbar_arrive_a(x_full + 8u * xs);
             }
           }
-          if (lane == 0) {
+          if (lane == 0 && !p.capstage) {
             const int ws = n_w % NWST;
             wt.mbar(w_empty + 8u * ws, ((n_w / NWST) & 1) ^ 1, 103);
             const uint32_t bytes = (uint32_t)cnt * wpair;
@@ -1301,8 +1408,29 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
 #pragma unroll
               for (int k = 0; k < T; ++k) y[jb][k] = 0.f;
             {
-              // two partial sums per round: 2 x T x OPL loads in flight
+              // four partial sums per round: 4 x T x OPL loads in flight (the accumulators of the pass are
+              // dead here, their registers hold the loads); summed in CTA order
               int cc = 0;
+              for (; cc + 3 < C; cc += 4) {
+                const float* s0 = Pbuf + ((size_t)cc * FZ_N + f) * T * OP + lane;
+                const float* s1 = s0 + (size_t)FZ_N * T * OP;
+                const float* s2 = s1 + (size_t)FZ_N * T * OP;
+                const float* s3 = s2 + (size_t)FZ_N * T * OP;
+                float t0[OPL][T], t1[OPL][T], t2[OPL][T], t3[OPL][T];
+#pragma unroll
+                for (int jb = 0; jb < OPL; ++jb)
+#pragma unroll
+                  for (int k = 0; k < T; ++k) {
+                    t0[jb][k] = __ldcg(s0 + k * OP + jb * 32);
+                    t1[jb][k] = __ldcg(s1 + k * OP + jb * 32);
+                    t2[jb][k] = __ldcg(s2 + k * OP + jb * 32);
+                    t3[jb][k] = __ldcg(s3 + k * OP + jb * 32);
+                  }
+#pragma unroll
+                for (int jb = 0; jb < OPL; ++jb)
+#pragma unroll
+                  for (int k = 0; k < T; ++k) y[jb][k] += (t0[jb][k] + t1[jb][k]) + (t2[jb][k] + t3[jb][k]);
+              }
               for (; cc + 1 < C; cc += 2) {
                 const float* s0 = Pbuf + ((size_t)cc * FZ_N + f) * T * OP + lane;
                 const float* s1 = s0 + (size_t)FZ_N * T * OP;

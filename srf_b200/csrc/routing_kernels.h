@@ -208,6 +208,8 @@ struct FusedParams {
   int nwst;                   // W ring stages
   int gtiles;                 // W tiles (hi + lo images) per ring stage = one bulk copy
   int wstage_bytes;           // ring stage stride
+  int capstage;               // 1: a ring stage holds exactly ONE capsule's tiles; one MMA issuer (warp 8), a
+                              // dedicated W producer (warp 9), stages released by the capsule's own commit
   int xtile_bytes;            // x ring stage stride (widest layer)
   int xstg_bytes;             // FP16 images: stride of the x loader's fp32 staging slots
   unsigned long long* dbg;    // optional phase timers [CTA][16] (clock64 sums), null = off

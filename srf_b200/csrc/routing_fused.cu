@@ -401,6 +401,16 @@ __device__ __forceinline__ void reg_fence16(float (&r)[16]) {
                  "+f"(r[7]), "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]),
                  "+f"(r[14]), "+f"(r[15])::"memory");
 }
+// acc[f] += a[f] * b[f] over 16 frames with packed fma.rn.f32x2: half the issue slots of
+// scalar FFMA (measured on cfg-3: 15.0 -> 14.3 ms, bit-identical results)
+__device__ __forceinline__ void fma16(float (&acc)[FZ_TF], const float (&a)[16], const float (&b)[FZ_TF]) {
+#pragma unroll
+  for (int f = 0; f < FZ_TF; f += 2) {
+    const float2 r = __ffma2_rn(make_float2(a[f], a[f + 1]), make_float2(b[f], b[f + 1]), make_float2(acc[f], acc[f + 1]));
+    acc[f] = r.x;
+    acc[f + 1] = r.y;
+  }
+}
 // second stage of the coupling softmax of 4 frames: exp(a - max), lane-partial normaliser, REDUX
 // add in Q26 fixed point (every term is <= 1; the normaliser keeps ~2^-21 relative accuracy)
 template <int OA>
@@ -492,14 +502,12 @@ __device__ __forceinline__ void fz_step_sa(const float (&va)[OPL][T4][FZ_TF], ui
       if (m + 1 < NTA) reg_fence16(u1);   // arrived with the same wait
       {
         const int jb = m / T4, k4 = m % T4;
-#pragma unroll
-        for (int f = 0; f < FZ_TF; ++f) pl[jb][f] = fmaf(u0[f], va[jb][k4][f], pl[jb][f]);
+        fma16(pl[jb], u0, va[jb][k4]);
       }
       if (m + 2 < NTA) tmem_ld16f(tbA + (uint32_t)((m + 2) * FZ_N), u0);
       if (m + 1 < NTA) {
         const int jb = (m + 1) / T4, k4 = (m + 1) % T4;
-#pragma unroll
-        for (int f = 0; f < FZ_TF; ++f) pl[jb][f] = fmaf(u1[f], va[jb][k4][f], pl[jb][f]);
+        fma16(pl[jb], u1, va[jb][k4]);
         if (m + 3 < NTA) tmem_ld16f(tbA + (uint32_t)((m + 3) * FZ_N), u1);
       }
       if (DOS && m == 0) fz_softmax_exp<OA>(a4, mi, ex, zi);
@@ -562,14 +570,12 @@ __device__ __forceinline__ void fz_step_b(float (&ta)[OPL][T4][FZ_TF], uint32_t 
     }
     {
       const int jb = m / T4, k4 = m % T4;
-#pragma unroll
-      for (int f = 0; f < FZ_TF; ++f) ta[jb][k4][f] = fmaf(cf[jb][f], u0[f], ta[jb][k4][f]);
+      fma16(ta[jb][k4], u0, cf[jb]);
     }
     if (m + 2 < NTA) tmem_ld16f(tbB + (uint32_t)((m + 2) * FZ_N), u0);
     if (m + 1 < NTA) {
       const int jb = (m + 1) / T4, k4 = (m + 1) % T4;
-#pragma unroll
-      for (int f = 0; f < FZ_TF; ++f) ta[jb][k4][f] = fmaf(cf[jb][f], u1[f], ta[jb][k4][f]);
+      fma16(ta[jb][k4], u1, cf[jb]);
       if (m + 3 < NTA) tmem_ld16f(tbB + (uint32_t)((m + 3) * FZ_N), u1);
     }
   }
@@ -1343,6 +1349,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               for (int f = 0; f < FZ_TF; ++f) ta[jb][k4][f] = 0.f;
 
           FZ_TK(0)
+          // a team none of whose 16 frames exists (batches of <= 16 utterances) only keeps the TMEM ring
+          // moving: its issue slots and TMEM bandwidth go to the other team
+          if (team_frames == 0) {
+            for (int n = 0; n < ncap; ++n) {
+              const uint32_t capA = n_t + (uint32_t)n;
+              wt.mbar(cap_done + 8u * (capA % FZ_CAP_RING), (capA / FZ_CAP_RING) & 1, 110);
+              __syncwarp();
+              if (lane == 0) mbar_arrive_a(t_empty + 8u * (uint32_t)(capA % NBUF));
+            }
+          } else
           // ---- the capsule loop, software-pipelined over two capsules ----
           for (int n = 0; n <= ncap; ++n) {
             const bool doA = n < ncap, doSB = n >= 1;
@@ -1382,7 +1398,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
           // ================= end of pass: exchange the partial sums through L2 =================
           ++epoch;
           v_target += team_frames;
-          {
+          if (team_frames != 0) {
             float* mine = Pbuf + (size_t)c * FZ_N * T * OP;
 #pragma unroll
             for (int jb = 0; jb < OPL; ++jb)
@@ -1408,29 +1424,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
 #pragma unroll
               for (int k = 0; k < T; ++k) y[jb][k] = 0.f;
             {
-              // four partial sums per round: 4 x T x OPL loads in flight (the accumulators of the pass are
-              // dead here, their registers hold the loads); summed in CTA order
+              // two partial sums per round: 2 x T x OPL loads in flight (four per round was measured: it helps
+              // units of 27 CTAs by 1 % and costs the cfg-3 shape 2 % through register allocation)
               int cc = 0;
-              for (; cc + 3 < C; cc += 4) {
-                const float* s0 = Pbuf + ((size_t)cc * FZ_N + f) * T * OP + lane;
-                const float* s1 = s0 + (size_t)FZ_N * T * OP;
-                const float* s2 = s1 + (size_t)FZ_N * T * OP;
-                const float* s3 = s2 + (size_t)FZ_N * T * OP;
-                float t0[OPL][T], t1[OPL][T], t2[OPL][T], t3[OPL][T];
-#pragma unroll
-                for (int jb = 0; jb < OPL; ++jb)
-#pragma unroll
-                  for (int k = 0; k < T; ++k) {
-                    t0[jb][k] = __ldcg(s0 + k * OP + jb * 32);
-                    t1[jb][k] = __ldcg(s1 + k * OP + jb * 32);
-                    t2[jb][k] = __ldcg(s2 + k * OP + jb * 32);
-                    t3[jb][k] = __ldcg(s3 + k * OP + jb * 32);
-                  }
-#pragma unroll
-                for (int jb = 0; jb < OPL; ++jb)
-#pragma unroll
-                  for (int k = 0; k < T; ++k) y[jb][k] += (t0[jb][k] + t1[jb][k]) + (t2[jb][k] + t3[jb][k]);
-              }
               for (; cc + 1 < C; cc += 2) {
                 const float* s0 = Pbuf + ((size_t)cc * FZ_N + f) * T * OP + lane;
                 const float* s1 = s0 + (size_t)FZ_N * T * OP;
@@ -1490,7 +1486,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
           if (lane == 0) wt.counter(cnt_v + team, v_target, 112);
           __syncwarp();
           FZ_TK(11)
-          if (last_pass && !p.sdr) {
+          if ((last_pass && !p.sdr) || team_frames == 0) {
             // DR: frames are independent, the next item starts from Vacc = 0
           } else {
 #pragma unroll

@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
           const uint32_t wstage16 = wstage >> 4, wpair16 = wpair >> 4, wtile16 = wtile >> 4, xtile16 = xtile >> 4;
           const int nks = KC / 2;
           const int nt = u_nt;
-          uint32_t n = 0;
+          uint32_t n = 0, ws = 0, w_par = 0, buf = 0, t_par = 0;
 #ifdef SRF_FUSED_TIMERS
           unsigned* trace = nullptr;
           if (p.dbg && (blockIdx.x == 0 || blockIdx.x == 80))
@@ -733,14 +733,17 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
             if (item.layer < 0) continue;
             const int total = nsteps * iters * u_ncap;
             for (int cc = 0; cc < total; ++cc, ++n) {
-              const uint32_t xs = n % (uint32_t)XST, buf = n % (uint32_t)NBUF, ws = n % (uint32_t)NWST;
+              // ring positions are carried, not divided out (NWST is a run-time value); the operands are
+              // checked first, the TMEM buffer last: it is what the issuer normally waits for, and the MMAs
+              // must go out as soon as the routing warps hand it back
+              const uint32_t xs = n % (uint32_t)XST;
               FZ_MK1(0)
               wt.mbar(x_full + 8u * xs, (n / XST) & 1, 104);
               ptx::fence_proxy_async();   // cp.async / st.shared wrote the tile through the generic proxy
               FZ_MK1(1)
-              wt.mbar(t_empty + 8u * buf, ((n / NBUF) & 1) ^ 1, 105);
+              wt.mbar(w_full + 8u * ws, w_par, 106);
               FZ_MK1(2)
-              wt.mbar(w_full + 8u * ws, (n / (uint32_t)NWST) & 1, 106);
+              wt.mbar(t_empty + 8u * buf, t_par ^ 1u, 105);
               FZ_MK1(5)
               ptx::tc_fence_after();
               const uint32_t d_base = tmem_base + buf * (uint32_t)TCOLS;
@@ -775,6 +778,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
               FZ_MK1(3)
               mma_commit_a(cap_done + 8u * (n % (uint32_t)FZ_CAP_RING));
               FZ_MK1(4)
+              if (++ws == (uint32_t)NWST) {
+                ws = 0;
+                w_par ^= 1u;
+              }
+              if (++buf == (uint32_t)NBUF) {
+                buf = 0;
+                t_par ^= 1u;
+              }
 #ifdef SRF_FUSED_TIMERS
               ++ncap_tr;
 #endif
@@ -784,7 +795,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
       } else if (ptx::elect_one()) {
         const uint32_t sW_a = ptx::smem_u32(sW);
         const uint64_t w_policy = l2_policy_evict_last();
-        uint32_t n = 0;
+        uint32_t n = 0, ws = 0;
         for (int it = 0; it < p.rounds; ++it) {
           const FusedItem item = p.items[(size_t)it * gridDim.x + blockIdx.x];
           if (item.layer < 0) continue;
@@ -793,13 +804,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) route_fused_kernel(const FusedP
           const int npass = nsteps * iters;
           for (int ps = 0; ps < npass; ++ps)
             for (int cc = 0; cc < u_ncap; ++cc, ++n) {
-              const uint32_t ws = n % (uint32_t)NWST;
               if (n >= (uint32_t)NWST) {
                 const uint32_t prev = n - (uint32_t)NWST;   // the stage's previous tenant has retired
                 wt.mbar(cap_done + 8u * (prev % FZ_CAP_RING), (prev / FZ_CAP_RING) & 1, 103);
               }
               mbar_expect_tx_a(w_full + 8u * ws, bytes);
               bulk_g2s_a(sW_a + ws * wstage, wsrc + (size_t)cc * bytes, bytes, w_full + 8u * ws, w_policy);
+              if (++ws == (uint32_t)NWST) ws = 0;
             }
         }
       }

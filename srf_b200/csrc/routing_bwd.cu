@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(MAXT, 1) dwdx_from_saved_kernel(const BwdParam
 // mma.sync.m16n8k8 TF32 with fp32 accumulation in registers:
 //   dW[(k,j)][l]  += g_u^T [(k,j)] [ft] . x  [ft] [l]      M = 32 D rows, N = d+1 (bias column), K = 32 frames
 //   dx [ft] [l]    = g_u   [ft] [(k,j)] . W_i [(k,j)] [l]  M = 32 frames, N = d,   K = 32 D
-// 8 warps; warp w owns the 16-row blocks w, w+8, ... of dW (all tiles of the CTA's frame split
+// 16 warps; warp w owns the 16-row blocks w, w+16, ... of dW (all tiles of the CTA's frame split
 // accumulate in its registers) and the K steps w, w+8, ... of dx (partials folded through shared memory).
 // g_u, x and W_i are rounded to TF32 (rna) when they are written to shared memory.
 // ---------------------------------------------------------------------------------------
@@ -1031,7 +1031,11 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float (&a)[
       : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
         "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
-constexpr int DWM_FT = 32, DWM_WARPS = 8;
+// 16 warps: the kernel is bound by the latency of the g_u rebuild (dependent L2 loads, then shared-memory
+// stores), not by a pipe -- 16 instead of 8 warps: 9.9 -> 8.8 ms per WSJ layer at 64 x 375 frames.  (Also
+// measured and dropped: two input capsules per CTA on 16-frame tiles sharing one pass over g_t / Vacc,
+// 10.7 ms; lane = output capsule rows with conflict-free stores, 9.7 ms with 8 warps, 9.2 with 16.)
+constexpr int DWM_FT = 32, DWM_WARPS = 16;
 }  // namespace
 
 size_t dwdx_mma_smem_bytes(int D, int d) {
@@ -1085,8 +1089,9 @@ __global__ void __launch_bounds__(DWM_WARPS * 32, 1) dwdx_from_saved_mma_kernel(
         if (l == d) {
           v = 1.f;
         } else if (l < d) {
-          const long long f = f0 + ft;
-          const int b = (int)(f / p.S), s_ = (int)(f - (long long)b * p.S);
+          // (frame indices fit 32 bits; a 64-bit division here was 8 % of the kernel's stall samples)
+          const unsigned f = (unsigned)(f0 + ft);
+          const int b = (int)(f / (unsigned)p.S), s_ = (int)(f - (unsigned)b * (unsigned)p.S);
           const int src = s_ - p.lpad + w;
           if (src >= 0 && src < p.S) v = p.emb[(((long long)b * p.S + src) * p.H + hc) * d + l];
         }

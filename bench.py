@@ -163,11 +163,11 @@ def run_reference_arm(args, w, rank, world):
   print(json.dumps(line), flush=True)
 
 
-def build_stack(w, dev, uhat, inn_dropout=0.1):
+def build_stack(w, dev, uhat, inn_dropout=0.1, bwd_uhat=None):
   from srf_b200 import RoutingStack
   return RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"], w["lpad"],
                       w["rpad"], w["iters"], w["sdr"], device=dev, seed=0, uhat_mode=uhat,
-                      inn_dropout=inn_dropout)
+                      inn_dropout=inn_dropout, bwd_uhat_mode=bwd_uhat)
 
 
 UHAT_DESC = {
@@ -408,8 +408,12 @@ def main():
     from srf_b200 import training
     w4 = WORKLOADS["cfg3"]
     B4, S4 = max(1, 64 // world), (w4["T"] + 3) // 4
-    train_mode = "bf16" if args.uhat in ("tf32", "f16", "bf16") else args.uhat
-    st4 = build_stack(w4, dev, train_mode)
+    # reduced-precision classes: forward in the bench mode (f16: the fused wavefront kernel), the backward
+    # recomputes u_hat with bf16 storage (the BPTT sweep streams it: half the bytes of fp32 u_hat)
+    fwd4 = args.uhat if args.uhat in ("f16", "tf32") else ("bf16" if args.uhat == "bf16" else args.uhat)
+    bwd4 = "bf16" if args.uhat in ("tf32", "f16", "bf16") else args.uhat
+    train_mode = fwd4 if fwd4 == bwd4 else "%s forward / %s backward recompute" % (fwd4, bwd4)
+    st4 = build_stack(w4, dev, fwd4, bwd_uhat=bwd4)
     tr4 = training.TrainStep(st4, B4 * world)
     g4 = torch.Generator().manual_seed(4 + rank)
     e4 = torch.randn(B4, S4, w4["PH"], w4["DIM"], generator=g4).to(dev)

@@ -1035,7 +1035,10 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float (&a)[
 // stores), not by a pipe -- 16 instead of 8 warps: 9.9 -> 8.8 ms per WSJ layer at 64 x 375 frames.  (Also
 // measured and dropped: two input capsules per CTA on 16-frame tiles sharing one pass over g_t / Vacc,
 // 10.7 ms; lane = output capsule rows with conflict-free stores, 9.7 ms with 8 warps, 9.2 with 16.)
-constexpr int DWM_FT = 32, DWM_WARPS = 16;
+#ifndef SRF_DWM_WARPS
+#define SRF_DWM_WARPS 16
+#endif
+constexpr int DWM_FT = 32, DWM_WARPS = SRF_DWM_WARPS;
 }  // namespace
 
 size_t dwdx_mma_smem_bytes(int D, int d) {

@@ -42,7 +42,7 @@ class RoutingStack:
   def __init__(self, enc_num: int, ph: int, ch: int, class_n: int, pd: int, cd: int, vd: int,
                lpad: int, rpad: int, iters: int, sdr: bool, inn_dropout: float = 0.1,
                device=None, seed: Optional[int] = None, uhat_mode: str = "exact",
-               length_eps: float = routing.LENGTH_EPS):
+               length_eps: float = routing.LENGTH_EPS, bwd_uhat_mode: Optional[str] = None):
     if enc_num < 1:
       raise ValueError("model_encoder_num must be >= 1")
     self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
@@ -52,6 +52,11 @@ class RoutingStack:
     self.class_n = class_n
     self.inn_dropout = float(inn_dropout)
     self.uhat_mode = uhat_mode
+    # mixed-precision training: the backward recomputes u_hat in this mode (None = the forward's).
+    # Nothing of size I*O*D is saved by the forward, so the two are independent: e.g. forward "f16" (the
+    # fused wavefront kernel) with backward "bf16" (bf16 u_hat stream for the BPTT sweep); the gradient then
+    # carries the backward mode's rounding class.
+    self.bwd_uhat_mode = bwd_uhat_mode
     self.length_eps = length_eps
     self.shapes = layer_shapes(enc_num, ph, ch, class_n, pd, cd, vd, self.window)
     g = torch.Generator(device="cpu")
@@ -163,6 +168,9 @@ class RoutingStack:
     data-parallel step launches that layer's all-reduce there) the layers are walked one
     srf_route_layer_bwd call at a time."""
     n = len(self._saved)
+    if self.bwd_uhat_mode is not None and self.bwd_uhat_mode != self.uhat_mode:
+      import dataclasses
+      self._saved = [(x, dataclasses.replace(a, uhat_mode=self.bwd_uhat_mode), r) for x, a, r in self._saved]
     names = lambda i: {"dW": "W%d" % i, "dbias": "b%d" % i, "dgamma": "ln_mid%d/gamma" % (i + 1),
                        "dbeta": "ln_mid%d/beta" % (i + 1), "dhead_gamma": "ln_output/gamma",
                        "dhead_beta": "ln_output/beta"}

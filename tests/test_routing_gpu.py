@@ -738,6 +738,43 @@ def test_stack_ctc_train_step_grads_match_autograd():
   assert rel_err(d_emb, emb.grad) < 5e-4
 
 
+def test_mixed_precision_train_step_f16_forward_bf16_backward():
+  """RoutingStack(uhat_mode="f16", bwd_uhat_mode="bf16") -- the bench's cfg-4 leg: the loss comes from the
+  fused FP16-image forward, the gradient from the bf16-recompute backward; it must sit in the bf16 class
+  (BWD_TOL) against autograd of the float64 oracle and equal the gradient of the pure bf16 mode up to the
+  difference of the two forwards' saved capsules."""
+  from srf_b200 import RoutingStack
+  L, PH, CH, class_n, DIM, lpad, rpad, iters, B, S = 3, 10, 6, 9, 8, 1, 1, 1, 3, 12
+  shapes = o.layer_shapes(L, PH, CH, class_n, DIM, DIM, DIM, lpad + rpad + 1)
+  p32 = o.init_params(shapes, class_n, seed=4, random_ln=True)
+  p = p32.to(torch.float64)
+  emb = torch.randn(B, S, PH, DIM, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+  labels = torch.tensor([[1, 3, 2, 0], [4, 4, 5, 1], [2, 6, 0, 0]])
+  in_len, lab_len = torch.tensor([12, 10, 9]), torch.tensor([3, 4, 2])
+  leaves = p.W + p.bias + [emb]
+  for t in leaves:
+    t.requires_grad_(True)
+  logits = o.route_stack(emb, p, lpad, rpad, iters, True)
+  loss = torch.nn.functional.ctc_loss(torch.log_softmax(logits, -1).transpose(0, 1), labels, in_len, lab_len,
+                                      blank=class_n - 1, reduction="sum", zero_infinity=True)
+  loss.backward()
+  got = {}
+  for name, fwd, bwd in (("mixed", "f16", "bf16"), ("bf16", "bf16", None)):
+    stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, True, seed=0, inn_dropout=0.0,
+                         uhat_mode=fwd, bwd_uhat_mode=bwd)
+    stack.load_oracle_params(p32)
+    got[name] = stack.ctc_train_step_grads(emb.detach().float().cuda(), labels.cuda(), in_len.cuda(), lab_len.cuda())
+    torch.cuda.synchronize()
+  m_loss, m_grads, m_demb = got["mixed"]
+  assert abs(m_loss.item() - loss.item()) / abs(loss.item()) < 5e-3      # forward: FP16-image class
+  tol = BWD_TOL["bf16"][1]
+  for i in range(L):
+    assert rel_err(m_grads["W%d" % i], p.W[i].grad) < tol, i
+    assert rel_err(m_grads["b%d" % i], p.bias[i].grad) < tol, i
+    assert rel_err(m_grads["W%d" % i], got["bf16"][1]["W%d" % i].cpu()) < tol, i
+  assert rel_err(m_demb, emb.grad) < tol
+
+
 def test_host_pipeline_matches_direct_forward():
   from srf_b200 import HostPipeline, RoutingStack
   stack = RoutingStack(3, 12, 6, 9, 8, 8, 8, 1, 1, 1, True, seed=3)

@@ -31,6 +31,8 @@ def main():
   ap.add_argument("--batch", type=int, default=64, help="global batch (utterances)")
   ap.add_argument("--frames", type=int, default=375, help="routing frames per utterance")
   ap.add_argument("--uhat", default="bf16", choices=["fp32", "tf32", "f16", "bf16", "fp32x3"])
+  ap.add_argument("--bwd-uhat", default=None, choices=["fp32", "tf32", "f16", "bf16", "fp32x3"],
+                  help="mode the backward recomputes u_hat in (default: the forward's)")
   ap.add_argument("--workload", default="cfg3")
   args = ap.parse_args()
   rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -43,7 +45,7 @@ def main():
   B, S = args.batch // world, args.frames
   stack = RoutingStack(w["L"], w["PH"], w["CH"], w["class_n"], w["DIM"], w["DIM"], w["DIM"], w["lpad"],
                        w["rpad"], w["iters"], w["sdr"], device=dev, seed=0, inn_dropout=0.1,
-                       uhat_mode=args.uhat)
+                       uhat_mode=args.uhat, bwd_uhat_mode=args.bwd_uhat)
   trainer = training.TrainStep(stack, args.batch)
   g = torch.Generator().manual_seed(1 + rank)
   emb = torch.randn(B, S, w["PH"], w["DIM"], generator=g).to(dev)

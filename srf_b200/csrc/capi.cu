@@ -61,6 +61,7 @@ struct srf_handle {
   size_t fz_arena_bytes = 0;
   std::vector<PackedWeights> fz_arena_keys;
   size_t l2_persist_max = 0, l2_window_max = 0;
+  bool l2_carved = false;   // the persisting-L2 carve-out is currently reserved (fused inference path)
   int no_fused = 0, force_fused = 0;
   void* fz_tab = nullptr;        // device: FusedLayer[] + FusedItem[] + counters + progress
   size_t fz_tab_bytes = 0;
@@ -166,16 +167,10 @@ extern "C" int srf_create(int device, srf_handle** out) {
   h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   // the persisting carve-out takes its share of L2 away from ALL normal traffic of the device (measured:
-  // the two-kernel fp32x3 path fell from 42 to 65 ms per cfg-3 step with it set), so it is reserved
-  // only when the experiment that uses it is switched on
-  if (!getenv("SRF_L2_WINDOW")) h->l2_persist_max = 0;
-  if (h->l2_persist_max > 0) {
-    DeviceGuard g(device);
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
-      cudaGetLastError();
-      h->l2_persist_max = 0;
-    }
-  }
+  // the two-kernel fp32x3 path fell from 42 to 65 ms per cfg-3 step with it set), so it is reserved lazily
+  // by the fused inference path (l2_carve) and given back by every other path; SRF_L2_WINDOW=0: never
+  if (const char* s = getenv("SRF_L2_WINDOW"))
+    if (s[0] == '0') h->l2_persist_max = 0;
   if (cudaHostAlloc((void**)&h->fz_host_abort, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
     *h->fz_host_abort = 0;
     if (cudaHostGetDevicePointer((void**)&h->fz_host_abort_dev, h->fz_host_abort, 0) != cudaSuccess)
@@ -192,9 +187,11 @@ extern "C" int srf_create(int device, srf_handle** out) {
   return 0;
 }
 
+static void l2_release(srf_handle* h);
 extern "C" int srf_destroy(srf_handle* h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
+  l2_release(h);
   for (auto& pw : h->packed) {
     if (pw.Wp) cudaFree(pw.Wp);
   }
@@ -653,6 +650,7 @@ static int compute_uhat(srf_handle* h, const srf_layer_desc* L, const UhatGeom& 
   return 0;
 }
 
+static void l2_release(srf_handle* h);
 extern "C" int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* L, float* out_uhat, void* stream_) {
   if (!h) return fail(nullptr, -1, "handle is NULL");
   if (!L || !out_uhat) return fail(h, -1, "layer descriptor or output is NULL");
@@ -662,6 +660,7 @@ extern "C" int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* L, float* out_u
     return fail(h, -2, "bad shape");
   if (L->O > 128 || L->D > 32 || L->d > 32) return fail(h, -3, "O > 128 or capsule dim > 32");
   DeviceGuard guard(h->device);
+  l2_release(h);
   cudaStream_t stream = (cudaStream_t)stream_;
   UhatGeom g;
   int rc = uhat_geometry(h, L, &g);
@@ -774,6 +773,31 @@ static int get_packed_fused(srf_handle* h, const srf_layer_desc* L, const FusedG
 
 // One fused launch: an SDR stack of n layers as a wavefront, or ONE DR layer (n == 1).
 // `layers` are validated, all fused-eligible, and agree on B, S, sdr, iters and uhat_mode.
+// Persisting-L2 carve-out for the packed weights of a fused multi-layer stack.  Without it the share of
+// the weight stream that misses L2 swings from run to run with the placement of the CTAs on the two dies
+// (ncu, cfg-3 f16: 10.4 and 21.3 GB of DRAM reads per step in two captures of the same build); with the
+// arena marked persisting it is 2.7 GB at the same speed (13.9 ms).  The carve-out is device-wide, so it
+// is reserved when the fused inference path runs and dropped again by every other path.
+static bool l2_carve(srf_handle* h) {
+  if (h->l2_persist_max == 0) return false;
+  if (!h->l2_carved) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
+      cudaGetLastError();
+      h->l2_persist_max = 0;
+      return false;
+    }
+    h->l2_carved = true;
+  }
+  return true;
+}
+static void l2_release(srf_handle* h) {
+  if (!h->l2_carved) return;
+  cudaCtxResetPersistingL2Cache();
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  cudaGetLastError();
+  h->l2_carved = false;
+}
+
 static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cudaStream_t stream) {
   int rc = fused_check_abort(h);
   if (rc) return rc;
@@ -1135,11 +1159,17 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
   }
   {
     KernelSpan span(h, 2, stream);
-    // SRF_L2_WINDOW=1: mark the weight arena as persisting in L2.  Measured on cfg-3: DRAM reads
-    // 39.0 -> 31.9 GB per step, but 19.1 -> 20.0 ms -- the 84 MB of weights are read by the SMs of both
-    // dies and do not fit either die's half of the L2 whatever the policy -- so it is off by default.
-    const void* win = n > 1 && h->l2_persist_max > 0 && getenv("SRF_L2_WINDOW") ? h->fz_arena : nullptr;
-    size_t win_bytes = win ? (arena_total < h->l2_window_max ? arena_total : h->l2_window_max) : 0;
+    // inference launches of a multi-layer stack whose packed weights fit the persisting carve-out (the
+    // FP16 images of cfg-3: 67.6 MB) mark the arena as persisting in L2 (see l2_carve); training forwards
+    // (out_raw requested) leave the L2 to the backward that follows.  (TF32 images, 101 MB, were measured
+    // in the first session: 39.0 -> 31.9 GB of DRAM reads but 19.1 -> 20.0 ms: not worth it.)
+    bool infer = n > 1 && arena_total <= h->l2_persist_max && arena_total <= h->l2_window_max;
+    for (int l = 0; l < n && infer; ++l)
+      if (layers[l].out_raw) infer = false;
+    const void* win = nullptr;
+    if (infer && l2_carve(h)) win = h->fz_arena;
+    else l2_release(h);
+    size_t win_bytes = win ? arena_total : 0;
     const float hit = win_bytes > h->l2_persist_max ? (float)h->l2_persist_max / (float)win_bytes : 1.0f;
     e = srf::launch_route_fused(p, T4, OPLM, kmode, grid, smem, stream, win, win_bytes, hit);
   }
@@ -1178,6 +1208,7 @@ static int route_layer_impl(srf_handle* h, const srf_layer_desc* L, cudaStream_t
       if (frc != FUSED_FALLBACK) return frc;
     }
   }
+  l2_release(h);   // the two-kernel paths want the whole L2 for the materialised u_hat
   const int window = L->lpad + L->rpad + 1;
   const int I = window * L->H;
   const int um = L->uhat_mode == SRF_UHAT_FP32 ? 0 : (L->uhat_mode == SRF_UHAT_BF16 ? 1 : 2);
@@ -1327,6 +1358,7 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   if (!L || !G) return fail(h, -1, "layer descriptor or grads is NULL");
   if (L->B == 0 || L->S == 0) return 0;
   DeviceGuard guard(h->device);
+  l2_release(h);   // the backward's kernels want the whole L2
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = validate_layer(h, L, false);
   if (rc) return rc;

@@ -94,7 +94,12 @@ typedef struct srf_layer_desc {
 /* library version (SRF_B200_VERSION of the built .so) */
 int srf_version(void);
 
-/* create / destroy the per-device workspace handle (host pointers) */
+/* create / destroy the per-device workspace handle (host pointers).  A handle owns scratch buffers that are
+ * reused, regrown and freed in stream order: calls may come on any stream -- a call on another stream than the
+ * previous one first waits (event) for everything the handle enqueued there, so streams sharing a handle
+ * serialise -- but one host thread at a time; concurrent host threads need one handle each.  The fused inference
+ * path of a multi-layer stack reserves the device's persisting-L2 carve-out for the packed weights and every
+ * other path gives it back (SRF_L2_WINDOW=0 in the environment of srf_create: never). */
 int srf_create(int device, srf_handle** out);
 int srf_destroy(srf_handle* h);
 
@@ -185,8 +190,10 @@ int srf_ctc_greedy_decode(srf_handle* h, const float* logits, const int32_t* len
  * unnormalised (log-softmax is applied inside, as TF does); labels [B,Lmax] int32; in_lens,
  * lab_lens [B] int32.  loss [B] receives the per-utterance negative log-likelihood; d_logits
  * [B,S,C] receives grad_scale * dloss/dlogits (grad_scale = 1/global_batch reproduces
- * tf.nn.compute_average_loss, trainer_sr.py:67-68).  Utterances with no feasible alignment get
- * loss 0 and a zero gradient.
+ * tf.nn.compute_average_loss, trainer_sr.py:67-68).  Utterances with no feasible alignment, or with a
+ * label outside [0, C) among their lab_lens labels, get loss 0 and a zero gradient (tf.nn.ctc_loss returns
+ * inf for the former and fails on the latter).  The per-class posterior sums are accumulated with
+ * shared-memory float atomics: d_logits is reproducible to rounding, not bitwise.
  */
 int srf_ctc_loss(srf_handle* h, const float* logits, const int32_t* labels, const int32_t* in_lens,
                  const int32_t* lab_lens, int32_t B, int32_t S, int32_t C, int32_t Lmax, int32_t blank,

@@ -62,6 +62,10 @@ struct srf_handle {
   std::vector<PackedWeights> fz_arena_keys;
   size_t l2_persist_max = 0, l2_window_max = 0;
   bool l2_carved = false;   // the persisting-L2 carve-out is currently reserved (fused inference path)
+  // the stream of the last compute call (see enter_stream)
+  cudaStream_t last_stream = nullptr;
+  bool have_stream = false;
+  cudaEvent_t xev = nullptr;
   int no_fused = 0, force_fused = 0;
   void* fz_tab = nullptr;        // device: FusedLayer[] + FusedItem[] + counters + progress
   size_t fz_tab_bytes = 0;
@@ -188,10 +192,24 @@ extern "C" int srf_create(int device, srf_handle** out) {
 }
 
 static void l2_release(srf_handle* h);
+// One stream at a time per handle: the scratch buffers (u_hat, workspaces, packed-weight caches, exchange
+// buffers) are reused, regrown and freed stream-ordered.  A call on another stream than the previous one first
+// waits for everything the handle enqueued there, so two streams can share a handle without overwriting or
+// freeing each other's scratch (they serialise); concurrent use from two host threads still needs two handles.
+static void enter_stream(srf_handle* h, cudaStream_t s) {
+  if (h->have_stream && h->last_stream != s) {
+    if (!h->xev && cudaEventCreateWithFlags(&h->xev, cudaEventDisableTiming) != cudaSuccess) h->xev = nullptr;
+    if (h->xev && cudaEventRecord(h->xev, h->last_stream) == cudaSuccess) cudaStreamWaitEvent(s, h->xev, 0);
+    cudaGetLastError();   // a stream the caller has destroyed meanwhile has nothing left to wait for
+  }
+  h->last_stream = s;
+  h->have_stream = true;
+}
 extern "C" int srf_destroy(srf_handle* h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
   l2_release(h);
+  if (h->xev) cudaEventDestroy(h->xev);
   for (auto& pw : h->packed) {
     if (pw.Wp) cudaFree(pw.Wp);
   }
@@ -248,6 +266,7 @@ extern "C" int srf_ctc_loss(srf_handle* h, const float* logits, const int32_t* l
     return fail(h, -2, "bad shape or blank index");
   DeviceGuard g(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  enter_stream(h, stream);
   const size_t need = (size_t)B * S * (2 * (size_t)Lmax + 1) * sizeof(float);
   if (need > h->ctc_ws_bytes) {
     if (h->ctc_ws) cudaFreeAsync(h->ctc_ws, stream);
@@ -299,6 +318,7 @@ extern "C" int srf_capsulate_fwd(srf_handle* h, const srf_frontend_desc* fe, voi
     return fail(h, -2, "front-end: the positional encoding needs an even model_caps_primary_num");
   DeviceGuard g(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  enter_stream(h, stream);
   const size_t need = srf::frontend_workspace_bytes(d);
   if (need > h->fe_ws_bytes) {
     if (h->fe_ws) cudaFreeAsync(h->fe_ws, stream);
@@ -662,6 +682,7 @@ extern "C" int srf_uhat_fwd(srf_handle* h, const srf_layer_desc* L, float* out_u
   DeviceGuard guard(h->device);
   l2_release(h);
   cudaStream_t stream = (cudaStream_t)stream_;
+  enter_stream(h, stream);
   UhatGeom g;
   int rc = uhat_geometry(h, L, &g);
   if (rc) return rc;
@@ -1358,6 +1379,7 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
   if (!L || !G) return fail(h, -1, "layer descriptor or grads is NULL");
   if (L->B == 0 || L->S == 0) return 0;
   DeviceGuard guard(h->device);
+  enter_stream(h, (cudaStream_t)stream_);
   l2_release(h);   // the backward's kernels want the whole L2
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = validate_layer(h, L, false);
@@ -1526,6 +1548,7 @@ extern "C" int srf_route_layer_bwd(srf_handle* h, const srf_layer_desc* L, const
 extern "C" int srf_route_layer_fwd(srf_handle* h, const srf_layer_desc* layer, void* stream) {
   if (!h) return fail(nullptr, -1, "handle is NULL");
   DeviceGuard g(h->device);
+  enter_stream(h, (cudaStream_t)stream);
   return route_layer_impl(h, layer, (cudaStream_t)stream);
 }
 
@@ -1535,6 +1558,7 @@ extern "C" int srf_route_stack_fwd(srf_handle* h, const srf_layer_desc* layers, 
   if (!layers || n_layers <= 0) return fail(h, -1, "no layers");
   DeviceGuard g(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  enter_stream(h, stream);
   const int B = layers[0].B, S = layers[0].S;
   size_t need = 0;
   for (int n = 0; n < n_layers; ++n) {

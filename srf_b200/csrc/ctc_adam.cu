@@ -107,6 +107,17 @@ ctc_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
   float* lsm = d_logits + (size_t)b * S * C;     // log-softmax, later the gradient
   float* alpha = alpha_ws + (size_t)b * S * NS;
   auto ext = [&](int s) { return (s & 1) ? lab[s >> 1] : blank; };
+  // labels outside [0, C) would index the log-softmax rows and the class accumulator out of bounds: such an
+  // utterance is treated like an infeasible alignment (loss 0, zero gradient)
+  {
+    int bad = 0;
+    for (int l = tid; l < L; l += CTC_THREADS) bad |= (lab[l] < 0 || lab[l] >= C);
+    if (__syncthreads_or(bad)) {
+      for (size_t e = tid; e < (size_t)S * C; e += CTC_THREADS) lsm[e] = 0.f;
+      if (tid == 0) loss[b] = 0.f;
+      return;
+    }
+  }
 
   // log-softmax of every frame (one warp per frame)
   for (int t = tid >> 5; t < S; t += CTC_THREADS >> 5) {

@@ -775,6 +775,25 @@ def test_mixed_precision_train_step_f16_forward_bf16_backward():
   assert rel_err(m_demb, emb.grad) < tol
 
 
+def test_two_streams_may_share_a_handle():
+  """Calls on alternating streams through ONE handle (shared scratch, regrown between the calls because the
+  batch sizes differ) give the results of the single-stream run: the handle orders them with an event."""
+  from srf_b200 import RoutingStack
+  stack = RoutingStack(3, 12, 6, 9, 8, 8, 8, 1, 1, 1, True, seed=3, uhat_mode="bf16")
+  g = torch.Generator().manual_seed(5)
+  batches = [torch.randn(b, 40, 12, 8, generator=g).cuda() for b in (2, 7, 3, 9, 4, 8)]
+  ref = [stack.forward(e).clone() for e in batches]
+  torch.cuda.synchronize()
+  s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+  outs = []
+  for n, e in enumerate(batches):
+    with torch.cuda.stream(s1 if n % 2 == 0 else s2):
+      outs.append(stack.forward(e))
+  torch.cuda.synchronize()
+  for a, b in zip(outs, ref):
+    assert torch.equal(a, b)
+
+
 def test_host_pipeline_matches_direct_forward():
   from srf_b200 import HostPipeline, RoutingStack
   stack = RoutingStack(3, 12, 6, 9, 8, 8, 8, 1, 1, 1, True, seed=3)

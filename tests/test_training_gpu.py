@@ -74,6 +74,26 @@ def test_ctc_infeasible_alignment_is_zeroed():
   assert loss.item() == 0.0 and torch.count_nonzero(d) == 0
 
 
+def test_ctc_out_of_range_labels_are_zeroed_and_leave_the_other_utterances_alone():
+  """A label outside [0, C) must not index out of bounds: that utterance gets loss 0 / zero gradient, the
+  others are unaffected; labels beyond lab_len are never looked at."""
+  from srf_b200 import training
+  g = torch.Generator().manual_seed(3)
+  logits = torch.randn(3, 9, 6, generator=g)
+  good = torch.tensor([[1, 2, 3, 0], [2, 2, 4, 1], [0, 1, 0, 0]])
+  bad = good.clone()
+  bad[1, 2] = 17                                     # >= C inside lab_len
+  bad[2, 3] = -5                                     # beyond lab_len[2] = 2: ignored
+  in_len, lab_len = torch.tensor([9, 9, 7]), torch.tensor([3, 4, 2])
+  l0, d0 = training.ctc_loss(logits.cuda(), good.cuda(), in_len.cuda(), lab_len.cuda())
+  l1, d1 = training.ctc_loss(logits.cuda(), bad.cuda(), in_len.cuda(), lab_len.cuda())
+  torch.cuda.synchronize()
+  assert l1[1].item() == 0.0 and torch.count_nonzero(d1[1]) == 0
+  for b in (0, 2):
+    assert abs(l1[b].item() - l0[b].item()) < 1e-5 * abs(l0[b].item())
+    assert (d1[b] - d0[b]).abs().max().item() < 1e-6
+
+
 def test_adam_matches_keras_formula_with_warmup_schedule():
   from srf_b200 import training
   rng = np.random.default_rng(0)

@@ -356,11 +356,17 @@ FUSED_LAYER_CASES = [
 ]
 
 
-@pytest.fixture
-def fused_handle(monkeypatch):
+@pytest.fixture(params=["policy", "capsule_stages", "tile_ring"])
+def fused_handle(monkeypatch, request):
+  """Forced fused kernel; the W ring layout by the library's policy, forced to capsule-sized stages (one MMA
+  issuer + W producer warp) and forced to the tile-granular ring (two issuers): both issue paths see every
+  shape, including stacks whose layers differ in tiles per capsule."""
   from srf_b200 import routing
   monkeypatch.setenv("SRF_FORCE_FUSED", "1")
+  if request.param != "policy":
+    monkeypatch.setenv("SRF_FUSED_CAPSTAGE", "1" if request.param == "capsule_stages" else "0")
   h = routing.Handle()
+  h.ring = request.param
   yield h
   h.close()
 
@@ -379,6 +385,10 @@ def test_fused_single_layer_matches_oracle(case, mode, fused_handle):
       caps, _ = routing.route_layer_fwd(emb.cuda(), a, handle=fused_handle)
       torch.cuda.synchronize()
       assert "route_fused_kernel" in fused_handle.last_kernel
+      if fused_handle.ring == "tile_ring":
+        assert "capstage" not in fused_handle.last_kernel
+      elif fused_handle.ring == "capsule_stages" and mode == "f16":
+        assert "capstage" in fused_handle.last_kernel   # three capsule-sized stages of FP16 images always fit
       assert rel_err(caps, ref) < (TENSOR_TOL if iters == 1 else TENSOR_TOL_ITER)[mode], (sdr, iters, last)
       if last:
         assert torch.count_nonzero(caps[:, :, 0]) == 0

@@ -867,8 +867,61 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
       Cl[best]++;
       budget--;
     }
+    // TPC alignment.  Blocks 2k and 2k+1 of the cooperative launch are the two SMs of one TPC
+    // (profiles/r2d_block_to_sm.txt).  Measured on cfg-3 (bench.py, ms per step; the layers 1-9 get seven CTAs
+    // each except two that get six and carry the most capsules per CTA): the two 6-CTA units on blocks that start
+    // at an even offset -- whole TPCs -- 13.28-13.33 (layers 2,3 / 4,5 / 6,7); starting at an odd offset, i.e.
+    // sharing a TPC with a unit of another layer at both ends, 13.69-13.79 (layers 3,4 / 5,6 / 3,6); the greedy
+    // order (last two layers) 13.69-13.74.  So, among layers of equal size (interchangeable for the greedy
+    // count), even-sized units are dealt to even block offsets and odd-sized ones to odd offsets.
+    if (!getenv("SRF_FUSED_NO_ALIGN")) {
+      std::vector<int> done(n, 0);
+      for (int l0 = 0; l0 < n; ++l0) {
+        if (done[l0]) continue;
+        std::vector<int> cls, cnt;
+        for (int l = l0; l < n; ++l)
+          if (!done[l] && geo[l].I == geo[l0].I) {
+            cls.push_back(l);
+            cnt.push_back(Cl[l]);
+            done[l] = 1;
+          }
+        if (cls.size() < 2) continue;
+        // offsets depend on everything before a layer: walk all layers, re-deal this class on the way
+        int off = 0;
+        size_t k = 0;
+        for (int l = 0; l < n; ++l) {
+          if (k < cls.size() && l == cls[k]) {
+            int pick = -1;
+            for (size_t c = 0; c < cnt.size(); ++c)
+              if (cnt[c] > 0 && ((cnt[c] ^ off) & 1) == 0) {   // same parity as the offset: even on even, odd on odd
+                pick = (int)c;
+                break;
+              }
+            if (pick < 0)
+              for (size_t c = 0; c < cnt.size(); ++c)
+                if (cnt[c] > 0) {
+                  pick = (int)c;
+                  break;
+                }
+            Cl[l] = cnt[pick];
+            cnt[pick] = 0;
+            ++k;
+          }
+          off += Cl[l];
+        }
+      }
+    }
     if (h->force_C > 0)
       for (int l = 0; l < n; ++l) Cl[l] = h->force_C < geo[l].I ? h->force_C : geo[l].I;
+    if (const char* ev = getenv("SRF_FUSED_PLAN")) {
+      // developer override: CTAs per layer, ':'-separated
+      int l = 0;
+      for (const char* q = ev; *q && l < n; ++l) {
+        Cl[l] = atoi(q);
+        while (*q && *q != ':') ++q;
+        if (*q == ':') ++q;
+      }
+    }
     int per_group = 0;
     for (int l = 0; l < n; ++l) {
       per_group += Cl[l];

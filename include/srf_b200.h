@@ -114,6 +114,10 @@ const char* srf_last_error(const srf_handle* h);
  * library's policy expects it to be faster than the two-kernel path (materialised u_hat); BF16 always
  * runs the two-kernel path, FP32 the CUDA-core kernel.  Results differ between the paths only within
  * the mode's rounding class.  Environment (read by srf_create): SRF_NO_FUSED=1 / SRF_FORCE_FUSED=1.
+ * Developer switches of the fused path, read at every call (none changes a result beyond the summation
+ * grouping of the plan): SRF_FUSED_CAPSTAGE=0/1 (tile-granular W ring with two MMA issuers / capsule-sized
+ * stages with one issuer), SRF_FUSED_NO_ALIGN=1 (greedy CTA plan without the TPC alignment),
+ * SRF_FUSED_PLAN=c0:c1:... (CTAs per layer of an SDR stack).
  * The fused kernel's waits are bounded: if one ever times out the launch drains and the NEXT call on
  * the handle returns 700 + wait-site code ("a fused routing launch timed out ...").
  */

@@ -917,7 +917,8 @@ static int fused_forward(srf_handle* h, const srf_layer_desc* layers, int n, cud
       // developer override: CTAs per layer, ':'-separated
       int l = 0;
       for (const char* q = ev; *q && l < n; ++l) {
-        Cl[l] = atoi(q);
+        const int c = atoi(q);
+        Cl[l] = c < 1 ? 1 : (c > geo[l].I ? geo[l].I : c);
         while (*q && *q != ':') ++q;
         if (*q == ':') ++q;
       }

@@ -16,8 +16,8 @@ from srf_b200 import routing
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 SCALE = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-TOL = {"fp32": 1e-4, "fp32x3": 1e-4, "tf32": 1e-2, "bf16": 2e-2}
-GTOL = {"fp32": 3e-4, "fp32x3": 3e-4, "tf32": 2e-2, "bf16": 8e-2}
+TOL = {"fp32": 1e-4, "fp32x3": 1e-4, "tf32": 1e-2, "f16": 1e-2, "bf16": 2e-2}
+GTOL = {"fp32": 3e-4, "fp32x3": 3e-4, "tf32": 2e-2, "f16": 2e-2, "bf16": 8e-2}
 
 
 def rel(a, ref):
@@ -26,7 +26,7 @@ def rel(a, ref):
 
 bad = done = skipped = 0
 for case in range(N):
-  mode = rng.choice(["fp32", "fp32x3", "tf32", "bf16"])
+  mode = rng.choice(["fp32", "fp32x3", "tf32", "f16", "bf16"])
   d = rng.choice([4, 8, 12, 16, 20, 24, 32]) if mode != "fp32" else rng.choice([3, 4, 8, 11, 16, 20, 32])
   D = rng.choice([4, 8, 12, 16, 20, 27, 32])
   O = rng.choice([2, 5, 9, 30, 32, 33, 40, 63, 64, 70, 100, 128])
@@ -55,8 +55,8 @@ for case in range(N):
   ref = o.route_layer(emb.double(), W.double(), bias.double(), lpad, rpad, iters, sdr, last)
   # conditioning of this instance: how much fp32 rounding (6e-8) is amplified by the routing passes
   amp = rel(o.route_layer(emb, W, bias, lpad, rpad, iters, sdr, last), ref) / 6e-8
-  pert = {"fp32": 1e-6, "fp32x3": 1e-6, "tf32": 1e-3, "bf16": 4e-3}[mode]   # u_hat perturbation
-  tol = max(TOL[mode] * (iters if mode in ("tf32", "bf16") else 1), 3 * amp * pert)
+  pert = {"fp32": 1e-6, "fp32x3": 1e-6, "tf32": 1e-3, "f16": 1e-3, "bf16": 4e-3}[mode]   # u_hat perturbation
+  tol = max(TOL[mode] * (iters if mode in ("tf32", "f16", "bf16") else 1), 3 * amp * pert)
   e1 = rel(caps, ref)
   ok = e1 < tol and torch.isfinite(caps).all().item()
   e2 = 0.0
@@ -75,7 +75,7 @@ for case in range(N):
       bad += 1
       print("BWD-ERROR", tag, str(e)[:100], flush=True)
       continue
-    gtol = max(GTOL[mode] * (iters if mode in ("tf32", "bf16") else 1), 10 * amp * pert)
+    gtol = max(GTOL[mode] * (iters if mode in ("tf32", "f16", "bf16") else 1), 10 * amp * pert)
     for name, lf in (("d_emb", leaves[0]), ("dW", leaves[1]), ("dbias", leaves[2])):
       if lf.grad.abs().max() > 0:
         e2 = max(e2, rel(got[name].reshape(lf.grad.shape), lf.grad))

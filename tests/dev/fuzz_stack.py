@@ -13,7 +13,7 @@ from srf_b200 import RoutingStack
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-TOL = {"exact": 1e-4, "fp32": 1e-4, "fp32x3": 1e-4, "tf32": 1e-2, "bf16": 2e-2}
+TOL = {"exact": 1e-4, "fp32": 1e-4, "fp32x3": 1e-4, "tf32": 1e-2, "f16": 1e-2, "bf16": 2e-2}
 
 
 def rel(a, ref):
@@ -22,7 +22,7 @@ def rel(a, ref):
 
 bad = done = skipped = 0
 for case in range(N):
-  mode = rng.choice(["exact", "fp32", "fp32x3", "tf32", "bf16"])
+  mode = rng.choice(["exact", "fp32", "fp32x3", "tf32", "f16", "bf16"])
   L = rng.randint(1, 3)
   DIM = rng.choice([4, 8, 12, 16, 20])
   PH, CH = rng.randint(2, 24), rng.randint(2, 40)
@@ -44,8 +44,8 @@ for case in range(N):
                       dropout_masks=None if masks is None else [m.double() for m in masks])
   ref32 = o.route_stack(emb, p32, lpad, rpad, iters, sdr, dropout_masks=masks)
   amp = rel(ref32, ref) / 6e-8
-  pert = {"exact": 1e-6, "fp32": 1e-6, "fp32x3": 1e-6, "tf32": 1e-3, "bf16": 4e-3}[mode]
-  tol = max(TOL[mode] * (iters if mode in ("tf32", "bf16") else 1), 3 * amp * pert)
+  pert = {"exact": 1e-6, "fp32": 1e-6, "fp32x3": 1e-6, "tf32": 1e-3, "f16": 1e-3, "bf16": 4e-3}[mode]
+  tol = max(TOL[mode] * (iters if mode in ("tf32", "f16", "bf16") else 1), 3 * amp * pert)
   stack = RoutingStack(L, PH, CH, class_n, DIM, DIM, DIM, lpad, rpad, iters, sdr, seed=0, uhat_mode=mode)
   stack.load_oracle_params(p32)
   try:

@@ -7,7 +7,7 @@ import traceback
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import srf_oracle as o  # noqa: E402
 from srf_b200 import RoutingStack, routing  # noqa: E402
